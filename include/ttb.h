@@ -1,0 +1,181 @@
+/* tortoise-b200: C-ABI of the sm_100a kernel library (libttb.so).
+ *
+ * The reference (neonbjb/tortoise-tts) has no FFI layer: its hot path is PyTorch modules calling
+ * ATen/cuBLAS/cuDNN. This header is the boundary a maintainer would bind instead (ctypes stub in
+ * INTEGRATION.md): every entry point takes raw device pointers, sizes and a cudaStream_t (as void*),
+ * returns 0 on success or a negative code (message via ttb_last_error()), and never throws.
+ * Each function cites the reference computation (file:line under /root/reference/tortoise) it replaces.
+ *
+ * Conventions: activations are TOKEN-MAJOR ([tokens, channels], channels contiguous) unless noted;
+ * "bf16" pointers are passed as void* to keep this header free of CUDA types; all kernels are enqueued
+ * on `stream` and do not synchronise.
+ */
+#ifndef TTB_H
+#define TTB_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* ttb_last_error(void);
+int ttb_version(void);
+/* 1 if the current device is compute capability 10.x (the only supported target), else 0 */
+int ttb_device_ok(void);
+
+/* ---------------------------------------------------------------- dense contraction (tcgen05) */
+enum { TTB_ACT_NONE = 0, TTB_ACT_GELU_NEW = 1, TTB_ACT_SILU = 2, TTB_ACT_GEGLU = 3, TTB_ACT_LRELU02 = 4 };
+
+typedef struct TtbGemmArgs {
+  const void* A;        /* bf16 [batch, rows, lda] activations (K contiguous) */
+  const void* W;        /* bf16 [N, taps*K] weights */
+  const float* bias;    /* [N] or NULL */
+  const float* residual;/* fp32 [batch, M, ldr] or NULL (added after the activation) */
+  float* out_f32;       /* fp32 [batch, M, ldo] or NULL */
+  void* out_bf16;       /* bf16 [batch, M, ldob] or NULL */
+  long long a_bstride, res_bstride, outf_bstride, outb_bstride; /* batch strides, in elements */
+  int lda, ldr, ldo, ldob;
+  int rows;             /* valid rows of A per batch item (conv zero-padding boundary) */
+  int M, N, K;          /* output rows per batch item, output columns, reduction per tap */
+  int taps, pad;        /* Conv1d kernel size (1 = plain GEMM) and left padding */
+  int batch;
+  int act;              /* TTB_ACT_* ; GEGLU expects W rows interleaved (u0,g0,u1,g1,..) and writes N/2 columns */
+  float alpha;          /* accumulator scale */
+  int tile_n;           /* 0 = auto, 64 or 128 */
+  int force_ref;        /* 1 = SIMT checker kernel (tests only) */
+} TtbGemmArgs;
+
+/* nn.Linear / HF Conv1D / nn.Conv1d(k=1,3) as one tcgen05 GEMM with fused bias/activation/residual.
+ * Replaces: GPT2 c_attn/c_proj/c_fc (HF 4.31 modeling_gpt2, via models/autoregressive.py:150-163),
+ * mel_head (autoregressive.py:42), CLVP to_q/k/v/to_out/FF (models/xtransformers.py:519-521,429-474),
+ * DiffusionTts convs (models/diffusion_decoder.py:83-103, models/arch_util.py:107-111),
+ * KernelPredictor.kernel_conv (models/vocoder.py:59-62). */
+int ttb_gemm(const TtbGemmArgs* args, void* stream);
+
+/* ---------------------------------------------------------------- normalisation */
+/* y = LN(x) (eps 1e-5), optionally followed by a second LN (gpt.ln_f then final_norm,
+ * autoregressive.py:42,174,348). x fp32 [M, D]; writes bf16 and/or fp32. */
+int ttb_layernorm(const float* x, int M, int D, const float* g1, const float* b1, const float* g2, const float* b2,
+                  void* out_bf16, float* out_f32, void* stream);
+/* x / max(||x|| * D^-0.5, 1e-8) * g   (xtransformers.py:335-344) */
+int ttb_rmsnorm(const float* x, int M, int D, const float* g, void* out_bf16, void* stream);
+/* GroupNorm32 over token-major x [B, S, C] (arch_util.py:21-41) fused with the consumers that follow it in
+ * ResBlock / AttentionBlock (diffusion_decoder.py:107-120): y = GN(x)*gamma+beta; if scale_shift:
+ * y = y*(1+scale[b,c]) + shift[b,c] (scale_shift fp32 [B, 2C] = [scale|shift]; when ss_row != NULL the table
+ * row *ss_row (device-side step counter) at stride ss_row_stride is used); if silu: y = SiLU(y).
+ * `partials` is a scratch buffer of B*groups*splits*2 floats. Output bf16 [B, S, ldo] and/or fp32. */
+int ttb_groupnorm(const float* x, int B, int S, int C, int groups, const float* gamma, const float* beta,
+                  const float* scale_shift, int ss_bstride, const int* ss_row, int ss_row_stride, int silu,
+                  float* partials, void* out_bf16, int ldo, float* out_f32, int ldof, void* stream);
+
+/* ---------------------------------------------------------------- attention */
+typedef struct TtbAttnArgs {
+  const void* qkv;      /* bf16 [nseq*T, ld]; q at col 0, k at col k_off, v at col v_off; head h at +64h */
+  void* out;            /* bf16 [nseq*T, ldo]; head h at col 64h */
+  const float* bias;    /* optional additive relative-position table fp32 [H, 2*T-1]: bias[h][j-i+T-1], or NULL */
+  int nseq, T, H;
+  int ld, ldo, k_off, v_off;
+  float scale;          /* applied to q.k */
+  int causal;
+} TtbAttnArgs;
+/* softmax(q k^T * scale + bias) v per (sequence, head), head_dim 64. Replaces QKVAttentionLegacy
+ * (arch_util.py:44-77), HF GPT2Attention._attn, and xtransformers Attention (xtransformers.py:660-712). */
+int ttb_attention(const TtbAttnArgs* args, void* stream);
+
+/* ---------------------------------------------------------------- autoregressive decode (UnifiedVoice) */
+typedef struct TtbArState {      /* device-resident, 64 ints */
+  int step;                      /* number of tokens already sampled per candidate */
+  int all_finished;
+  int reserved[62];
+} TtbArState;
+
+/* emb[b] = mel_embedding[tok[b]] + mel_pos_embedding[pos(step)] (autoregressive.py:145-149). pos_mode 0 =
+ * train-consistent (j), 1 = reference kv-cache rule (j+1). tokens = codes[b, step-1]. */
+int ttb_ar_embed_step(const int* codes, int ld_codes, const TtbArState* state, const float* mel_emb,
+                      const float* mel_pos, int B, int D, int pos_mode, float* x, void* stream);
+/* One-query attention over [shared prefix | candidate KV] for every (candidate, head); appends the new K/V.
+ * prefix_k/v: bf16 [H, P, 64]; cand_k/v: bf16 [B, H, Nmax, 64]; qkv bf16 [B, 3*H*64]. */
+int ttb_ar_decode_attention(const void* qkv, const void* prefix_k, const void* prefix_v, void* cand_k, void* cand_v,
+                            const TtbArState* state, int B, int H, int P, int Nmax, void* out, void* stream);
+/* copy K/V of the prompt from a qkv buffer [P, 3*H*64] into the prefix cache [H, P, 64] */
+int ttb_ar_store_prefix(const void* qkv, int P, int H, void* prefix_k, void* prefix_v, void* stream);
+/* HF sample() step, fused: repetition penalty over the ids seen (incl. fake prompt ids 1 and 8192), temperature,
+ * top-k, top-p, softmax, inverse-CDF draw with the supplied uniform, stop-token bookkeeping
+ * (in-tree copy of HF 4.31: models/stream_generator.py:943-1000). logits fp32 [B or 1, V] (ld_logits = 0
+ * broadcasts row 0); uniforms [B, ld_u] indexed by state->step; seen: bitmask [B, ceil(V/32)];
+ * codes int32 [B, ld_codes]; finished int32 [B]. Advances state->step when `advance` != 0. */
+int ttb_ar_sample(const float* logits, int ld_logits, int V, int B, const float* uniforms, int ld_u, uint32_t* seen,
+                  int* codes, int ld_codes, int* finished, TtbArState* state, float temperature, int top_k, float top_p,
+                  float rep_penalty, int stop_token, int advance, void* stream);
+/* fix_autoregressive_output (api.py:87-114) for every row + calm-token trim length (api.py:547-556) */
+int ttb_ar_fix_codes(int* codes, int B, int L, int stop_token, int* trim_len, void* stream);
+/* rows of an embedding table + optional positional table -> fp32 [n, D]; ids int32, pos int32 (or NULL) */
+int ttb_embed(const int* ids, const int* pos, int n, int D, const float* table, const float* pos_table, float* out,
+              void* stream);
+
+/* ---------------------------------------------------------------- CLVP */
+/* rotary (dim 32) on the first 32 dims of every head of q, k AND v (xtransformers.py:625-629,264-286);
+ * qkv bf16 [nseq*T, 3*H*64] in place. */
+int ttb_clvp_rotary(void* qkv, int nseq, int T, int H, void* stream);
+/* LayerNorm + mean over the sequence (xtransformers.py:1234, clvp.py:15-17,123-124): x fp32 [nseq*T, D] -> [nseq, D] */
+int ttb_clvp_pool(const float* x, int nseq, int T, int D, const float* g, const float* b, float* out, void* stream);
+/* latent = normalize(pooled @ W^T) ; score[b] = <latent[b], text_latent> * exp(temperature) (clvp.py:126-135).
+ * If text_latent == NULL only the normalised latents are written. */
+int ttb_clvp_project(const float* pooled, int n, int D, const float* W, float* latents, const float* text_latent,
+                     float temp_exp, float* scores, void* stream);
+
+/* ---------------------------------------------------------------- diffusion */
+/* timestep_embedding(t, C) (diffusion_decoder.py:21-39) for n timesteps -> fp32 [n, C] */
+int ttb_timestep_embedding(const int* t, int n, int C, float* out, void* stream);
+/* y[m, :] = act_in(x[m, :]) @ W^T + b for small M (emb layers / time_embed); fp32 SIMT */
+int ttb_linear_small(const float* x, int M, int K, const float* W, const float* b, int N, int silu_in, int silu_out,
+                     float* out, void* stream);
+/* nearest-neighbour upsample along tokens (F.interpolate(mode='nearest'), diffusion_decoder.py:249) fused with the
+ * conditioning scale/shift: out[s, c] = x[floor(s*N/S), c] ; x fp32 [N, C] -> bf16/fp32 [S, ld] */
+int ttb_interp_nearest(const float* x, int N, int S, int C, void* out_bf16, int ldo, float* out_f32, int ldof, void* stream);
+typedef struct TtbDiffStepArgs {
+  const float* model_out;   /* fp32 [nb, S, ld_out]: batch 0 = conditional (eps | var), batch 1 = unconditional */
+  long long out_bstride; int ld_out;
+  float* x;                 /* fp32 [S, C] current sample, updated in place */
+  void* x_bf16; int ld_xb;  /* bf16 copy [S, ld_xb] (zero-padded channels) for the next inp_block conv, or NULL */
+  const float* noise;       /* fp32 [iters, S, C] pre-drawn, indexed by call order */
+  const float* tables;      /* fp32 [6, iters]: sqrt_recip_ac, sqrt_recipm1_ac, post_logvar_clipped, log_betas, coef1, coef2 */
+  const int* step;          /* device counter: call index (0 .. iters-1); spaced index i = iters-1-call */
+  int S, C, iters;
+  int cond_free; float cond_free_k;
+  float* mel_out;           /* optional fp32 [C, S] channel-major denormalised mel written when i == 0 */
+} TtbDiffStepArgs;
+/* p_mean_variance + p_sample epilogue (utils/diffusion.py:340-418,487-531): CFG mix with linear ramp,
+ * learned-range variance, eps->x0 clamp, posterior mean, ancestral noise; denormalize_tacotron_mel on the
+ * last step (utils/audio.py:63-64). */
+int ttb_diffusion_step(const TtbDiffStepArgs* args, void* stream);
+/* misc small device helpers */
+int ttb_counter_add(int* counter, int delta, void* stream);
+int ttb_transpose_f32(const float* in, int R, int Cc, float* out, void* stream);           /* [R, C] -> [C, R] */
+/* fp32 [R, Cc] (row stride ld_in) -> bf16 [R, ncols_out] (row stride ldo), columns >= Cc zero-filled */
+int ttb_cast_pad_bf16(const float* in, int R, int Cc, int ld_in, void* out, int ldo, int ncols_out, void* stream);
+int ttb_broadcast_rows(const float* row, int R, int Cc, float* out_f32, void* out_bf16, int ldo, void* stream);
+
+/* ---------------------------------------------------------------- UnivNet vocoder (channel-major fp32 [C, L]) */
+/* Conv1d, small channel counts, zero or reflect padding, optional LeakyReLU on input/output, optional residual add
+ * (vocoder.py:40-64 KernelPredictor convs, 146-153 dilated conv, 245-265 conv_pre/conv_post). tanh_out for conv_post. */
+int ttb_voc_conv1d(const float* x, int Cin, int L, const float* w, const float* b, int Cout, int ksize, int dilation,
+                   int reflect, float lrelu_in, float lrelu_out, int tanh_out, const float* residual, float* out,
+                   void* stream);
+/* LeakyReLU + ConvTranspose1d(k = 2*stride, stride, padding = stride/2 + stride%2, output_padding = stride%2)
+ * (vocoder.py:138-142). w: [Cin, Cout, 2*stride]. x [C, L] -> [C, L*stride] */
+int ttb_voc_convt(const float* x, int C, int L, const float* w, const float* b, int stride, float lrelu_in, float* out,
+                  void* stream);
+/* location-variable convolution + gated activation, fused (vocoder.py:169-178,182-216):
+ *   o[oc, f*hop+s] = sum_{i,k} ypad[i, f*hop+s+k] * K[f][i][k][oc] + Bias[f][oc];  x += sigmoid(o[:C]) * tanh(o[C:])
+ * y [C, L] (L = F*hop); kernels fp32 [F, ldk] with this layer's block at column koff laid out [i][k][oc];
+ * bias fp32 [F, ldb] at column boff laid out [oc]. */
+int ttb_voc_lvc_gate(const float* y, int C, int L, int hop, const float* kernels, int ldk, int koff, const float* bias,
+                     int ldb, int boff, float* x, void* stream);
+/* channel-major fp32 [C, L] -> token-major bf16 [L, ldo] (feeds the kernel-predictor GEMM) */
+int ttb_voc_to_tokens_bf16(const float* x, int C, int L, void* out, int ldo, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

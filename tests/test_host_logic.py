@@ -1,0 +1,59 @@
+"""CPU: host-side logic of the engine (schedule tables, relative-position tables, weight regrouping)."""
+import numpy as np
+import torch
+
+from tortoise_tts_b200.config import ModelConfig
+from tortoise_tts_b200 import diffusion_engine as de
+
+
+def test_schedule_matches_oracle():
+    from oracle import diffusion as od
+    for iters in (5, 30, 80, 200, 400):
+        tmap, tables = de.make_schedule(iters)
+        s = od.make_schedule(iters)
+        assert list(tmap) == list(s["timestep_map"])
+        names = ["sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_log_variance_clipped",
+                 "log_betas", "posterior_mean_coef1", "posterior_mean_coef2"]
+        for r, n in enumerate(names):
+            assert np.array_equal(tables[r], s[n].astype(np.float32)), n
+
+
+def test_rel_pos_table_matches_oracle():
+    from oracle import diffusion as od
+    torch.manual_seed(0)
+    emb = torch.randn(32, 4)
+    T = 37
+    tab = de._rel_pos_table(emb, T, 8.0)          # [H, 2T-1]
+    full = od.rel_pos_bias(emb, T, 8.0)           # [H, T, T]
+    for i in (0, 5, 36):
+        for j in (0, 17, 36):
+            assert torch.allclose(tab[:, j - i + T - 1], full[:, i, j])
+
+
+def test_groups_rule():
+    from oracle import diffusion as od
+    for C in (16, 64, 128, 1024, 2048):
+        assert de._groups_for(C) == od.groups_for(C)
+
+
+def test_qkv_regroup():
+    """per-head [q|k|v] rows -> [q heads | k heads | v heads] (arch_util.py:60-63)."""
+    C, H = 128, 2
+    ch = C // H
+    idx = torch.arange(3 * C).reshape(H, 3, ch).permute(1, 0, 2).reshape(-1)
+    # new row (which=1 (k), head=1, d=5) must come from old row head*192 + which*64 + d
+    assert int(idx[1 * C + 1 * ch + 5]) == 1 * 3 * ch + 1 * ch + 5
+
+
+def test_presets_match_reference_values():
+    from tortoise_tts_b200.api import PRESETS
+    assert PRESETS["standard"] == {"num_autoregressive_samples": 256, "diffusion_iterations": 200}
+    assert PRESETS["ultra_fast"]["cond_free"] is False
+    assert PRESETS["high_quality"]["diffusion_iterations"] == 400
+
+
+def test_synth_layout_param_counts():
+    from tortoise_tts_b200.synth import synth_all
+    sds = synth_all(ModelConfig.small())
+    assert "gpt.h.1.mlp.c_proj.weight" in sds["autoregressive"]
+    assert sds["vocoder"]["res_stack.0.kernel_predictor.kernel_conv.weight_v"].shape == (24576, 64, 3)

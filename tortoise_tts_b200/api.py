@@ -1,0 +1,191 @@
+"""Drop-in facade for `tortoise.api.TextToSpeech` (tortoise/api.py:174-609) on the sm_100a engine.
+
+Same constructor / `tts()` / `tts_with_preset()` signatures, presets, return types and checkpoint layout
+(`models_dir` with autoregressive.pth, diffusion_decoder.pth, clvp2.pth, vocoder.pth). Everything between the
+tokenizer and `wav.cpu()` runs in libttb.so; there is no PyTorch/CPU fallback for the hot path.
+
+Differences that are deliberate: all candidates are decoded in one batch (the reference loops over
+`autoregressive_batch_size` chunks and silently drops the remainder), models stay resident on the device, and the
+sampling / diffusion randomness comes from device generators seeded by `use_deterministic_seed`.
+"""
+import os
+import random
+from time import time
+
+import torch
+
+from .config import ModelConfig
+from .ar_engine import AREngine
+from .clvp_engine import CLVPEngine
+from .diffusion_engine import DiffusionEngine
+from .vocoder_engine import VocoderEngine
+from . import lib
+
+DEFAULT_MODELS_DIR = os.path.join(os.path.expanduser("~"), ".cache", "tortoise", "models")
+MODELS_DIR = os.environ.get("TORTOISE_MODELS_DIR", DEFAULT_MODELS_DIR)
+MODELS = ("autoregressive.pth", "classifier.pth", "clvp2.pth", "cvvp.pth", "diffusion_decoder.pth", "vocoder.pth",
+          "rlg_auto.pth", "rlg_diffuser.pth")
+
+PRESETS = {  # api.py:320-329
+    "ultra_fast": {"num_autoregressive_samples": 16, "diffusion_iterations": 30, "cond_free": False},
+    "fast": {"num_autoregressive_samples": 96, "diffusion_iterations": 80},
+    "standard": {"num_autoregressive_samples": 256, "diffusion_iterations": 200},
+    "high_quality": {"num_autoregressive_samples": 256, "diffusion_iterations": 400},
+}
+
+
+def get_model_path(model_name, models_dir=MODELS_DIR):
+    if model_name not in MODELS:
+        raise ValueError(f"Model {model_name} not found in available models.")
+    path = os.path.join(models_dir, model_name)
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} missing (this build is offline: place the reference checkpoints there)")
+    return path
+
+
+def pad_or_truncate(t, length):
+    if t.shape[-1] == length:
+        return t
+    if t.shape[-1] < length:
+        return torch.nn.functional.pad(t, (0, length - t.shape[-1]))
+    return t[..., :length]
+
+
+class _Tokenizer:
+    """VoiceBpeTokenizer.encode (utils/tokenizer.py:172-185) with the basic cleaner chain. The BPE vocabulary is the
+    reference's data/tokenizer.json (an asset, not code): pass `tokenizer_vocab_file` or set TORTOISE_TOKENIZER_JSON."""
+
+    def __init__(self, vocab_file=None):
+        from tokenizers import Tokenizer
+        vocab_file = vocab_file or os.environ.get("TORTOISE_TOKENIZER_JSON")
+        if vocab_file is None or not os.path.exists(vocab_file):
+            raise FileNotFoundError("tokenizer.json not found: pass tokenizer_vocab_file=... (reference asset "
+                                    "tortoise/data/tokenizer.json) or call tts() with pre-tokenised `text_tokens`")
+        self.tok = Tokenizer.from_file(vocab_file)
+
+    def encode(self, txt):
+        import re
+        txt = re.sub(r"\s+", " ", txt.lower()).replace('"', "")
+        txt = txt.replace(" ", "[SPACE]")
+        return self.tok.encode(txt).ids
+
+
+class TextToSpeech:
+    def __init__(self, autoregressive_batch_size=None, models_dir=MODELS_DIR, enable_redaction=True, kv_cache=False,
+                 use_deepspeed=False, half=False, device=None, tokenizer_vocab_file=None, tokenizer_basic=False,
+                 state_dicts=None, config: ModelConfig = None):
+        """`state_dicts` (dict with keys autoregressive/diffusion/clvp/vocoder) bypasses models_dir (synthetic
+        checkpoints); `config` overrides the full-size ModelConfig (tests)."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("tortoise_tts_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        lib.load()
+        self.models_dir = models_dir
+        self.autoregressive_batch_size = autoregressive_batch_size  # accepted for API parity; one batch is used
+        self.enable_redaction = False  # wav2vec redaction is out of scope
+        self.kv_cache = kv_cache
+        self.device = torch.device(device if device is not None else "cuda")
+        self.cfg = config or ModelConfig.full()
+        self._tok_file = tokenizer_vocab_file
+        self._tokenizer = None
+        if state_dicts is None:
+            state_dicts = {
+                "autoregressive": torch.load(get_model_path("autoregressive.pth", models_dir), map_location="cpu"),
+                "diffusion": torch.load(get_model_path("diffusion_decoder.pth", models_dir), map_location="cpu"),
+                "clvp": torch.load(get_model_path("clvp2.pth", models_dir), map_location="cpu"),
+                "vocoder": torch.load(get_model_path("vocoder.pth", models_dir), map_location="cpu")["model_g"],
+            }
+        self.autoregressive = AREngine(state_dicts["autoregressive"], self.cfg, self.device)
+        self.clvp = CLVPEngine(state_dicts["clvp"], self.cfg, self.device)
+        self.diffusion = DiffusionEngine(state_dicts["diffusion"], self.cfg, self.device)
+        self.vocoder = VocoderEngine(state_dicts["vocoder"], self.cfg, self.device)
+        self.last_timings = {}
+
+    @property
+    def tokenizer(self):
+        if self._tokenizer is None:
+            self._tokenizer = _Tokenizer(self._tok_file)
+        return self._tokenizer
+
+    def deterministic_state(self, seed=None):
+        seed = int(time()) if seed is None else seed
+        torch.manual_seed(seed)
+        random.seed(seed)
+        return seed
+
+    def tts_with_preset(self, text, preset="fast", **kwargs):
+        settings = {"temperature": .8, "length_penalty": 1.0, "repetition_penalty": 2.0, "top_p": .8,
+                    "cond_free_k": 2.0, "diffusion_temperature": 1.0}
+        settings.update(PRESETS[preset])
+        settings.update(kwargs)
+        return self.tts(text, **settings)
+
+    def tts(self, text, voice_samples=None, conditioning_latents=None, k=1, verbose=True, use_deterministic_seed=None,
+            return_deterministic_state=False, num_autoregressive_samples=512, temperature=.8, length_penalty=1,
+            repetition_penalty=2.0, top_p=.8, max_mel_tokens=500, cvvp_amount=.0, diffusion_iterations=100,
+            cond_free=True, cond_free_k=2, diffusion_temperature=1.0, text_tokens=None, top_k=50, **hf_generate_kwargs):
+        """≙ TextToSpeech.tts (api.py:334-597). `text_tokens` (list of BPE ids) may be given instead of `text`."""
+        if cvvp_amount != 0:
+            raise NotImplementedError("CVVP is out of scope of this engine (disabled by default in the reference)")
+        if voice_samples is not None:
+            raise NotImplementedError("get_conditioning_latents is a 'next' row (SURVEY §8f-1); pass conditioning_latents")
+        if hf_generate_kwargs:
+            raise TypeError(f"unsupported generate kwargs: {sorted(hf_generate_kwargs)}")
+        if conditioning_latents is None:
+            raise NotImplementedError("random-voice latents need rlg_*.pth; pass conditioning_latents")
+        seed = self.deterministic_state(seed=use_deterministic_seed)
+        dev = self.device
+        if text_tokens is None:
+            text_tokens = self.tokenizer.encode(text)
+        toks = [int(t) for t in text_tokens] + [0]            # F.pad(text_tokens, (0, 1)) (api.py:391)
+        assert len(toks) < 400, "Too much text provided. Break the text up into separate segments and re-try inference."
+        auto_cond, diff_cond = conditioning_latents
+        auto_cond = auto_cond.to(dev).float().reshape(-1)
+        diff_cond = diff_cond.to(dev).float().reshape(-1)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        with torch.no_grad():
+            ev[0].record()
+            codes = self.autoregressive.generate(auto_cond, toks, num_autoregressive_samples, max_mel_tokens, seed=seed,
+                                                 temperature=temperature, top_k=top_k, top_p=top_p,
+                                                 repetition_penalty=repetition_penalty,
+                                                 pos_mode="ref_kv_quirk" if self.kv_cache else "train_consistent")
+            B, L = codes.shape
+            trim = torch.empty(B, dtype=torch.int32, device=dev)
+            lib.ar_fix_codes(codes, B, L, self.cfg.stop_mel_token, trim)
+            ev[1].record()
+            scores = self.clvp.scores(toks, codes)
+            best = torch.topk(scores, k=k).indices
+            best_codes = codes[best]
+            ev[2].record()
+            best_latents = self.autoregressive.latents(auto_cond, toks, best_codes)
+            ev[3].record()
+            trims = trim[best].tolist()
+            wavs = []
+            g = torch.Generator(device=dev)
+            g.manual_seed(seed)
+            t_diff = t_voc = 0.0
+            for b in range(best_codes.shape[0]):
+                lat = best_latents[b, : trims[b]]
+                S = lat.shape[0] * 4 * 24000 // 22050
+                noise0 = torch.randn(100, S, generator=g, device=dev) * diffusion_temperature
+                step_noise = torch.randn(diffusion_iterations, 100, S, generator=g, device=dev)
+                e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                e0.record()
+                mel = self.diffusion.sample(lat, diff_cond, diffusion_iterations, noise0, step_noise, cond_free=cond_free,
+                                            cond_free_k=cond_free_k)
+                e1.record()
+                # the reference draws the vocoder noise on the CPU (vocoder.py:307); device draw here
+                z = torch.randn(64, S + 10, generator=g, device=dev)
+                wav = self.vocoder.inference(mel, z)
+                e2.record()
+                wavs.append((wav, e0, e1, e2))
+            res = []
+            for wav, e0, e1, e2 in wavs:
+                res.append(wav.reshape(1, 1, -1).cpu())          # wav.cpu() synchronises, as in the reference
+                t_diff += e0.elapsed_time(e1)
+                t_voc += e1.elapsed_time(e2)
+            self.last_timings = {"ar_ms": ev[0].elapsed_time(ev[1]), "clvp_ms": ev[1].elapsed_time(ev[2]),
+                                 "latents_ms": ev[2].elapsed_time(ev[3]), "diffusion_ms": t_diff, "vocoder_ms": t_voc}
+        out = res if len(res) > 1 else res[0]
+        if return_deterministic_state:
+            return out, (seed, text, voice_samples, conditioning_latents)
+        return out

@@ -1,0 +1,289 @@
+"""UnifiedVoice autoregressive stage on the sm_100a kernels (hot loop 1 + latents).
+
+Host side mirrors `UnifiedVoice.inference_speech` / `UnifiedVoice.forward(return_latent=True)`
+(tortoise/models/autoregressive.py:535-563, 454-512): same inputs (conditioning latent, zero-padded text
+tokens), same outputs (codes / latents). All arithmetic runs in libttb.so; torch is used for allocation,
+weight packing at load time, and CUDA-graph capture of the decode step.
+"""
+import torch
+
+from . import lib
+from .config import ModelConfig
+
+
+def _bf(t, dev):
+    return t.to(device=dev, dtype=torch.bfloat16).contiguous()
+
+
+def _f(t, dev):
+    return t.to(device=dev, dtype=torch.float32).contiguous()
+
+
+class ARWeights:
+    """Packs `autoregressive.pth`: HF Conv1D weights [in,out] are transposed to K-major bf16."""
+
+    def __init__(self, sd, cfg: ModelConfig, dev):
+        D = cfg.ar_dim
+        self.layers = []
+        for l in range(cfg.ar_layers):
+            p = f"gpt.h.{l}."
+            self.layers.append(dict(
+                ln1_g=_f(sd[p + "ln_1.weight"], dev), ln1_b=_f(sd[p + "ln_1.bias"], dev),
+                wqkv=_bf(sd[p + "attn.c_attn.weight"].t(), dev), bqkv=_f(sd[p + "attn.c_attn.bias"], dev),
+                wproj=_bf(sd[p + "attn.c_proj.weight"].t(), dev), bproj=_f(sd[p + "attn.c_proj.bias"], dev),
+                ln2_g=_f(sd[p + "ln_2.weight"], dev), ln2_b=_f(sd[p + "ln_2.bias"], dev),
+                wfc=_bf(sd[p + "mlp.c_fc.weight"].t(), dev), bfc=_f(sd[p + "mlp.c_fc.bias"], dev),
+                wproj2=_bf(sd[p + "mlp.c_proj.weight"].t(), dev), bproj2=_f(sd[p + "mlp.c_proj.bias"], dev)))
+        self.lnf_g, self.lnf_b = _f(sd["gpt.ln_f.weight"], dev), _f(sd["gpt.ln_f.bias"], dev)
+        self.fn_g, self.fn_b = _f(sd["final_norm.weight"], dev), _f(sd["final_norm.bias"], dev)
+        self.text_emb = _f(sd["text_embedding.weight"], dev)
+        self.mel_emb = _f(sd["mel_embedding.weight"], dev)
+        self.mel_pos = _f(sd["mel_pos_embedding.emb.weight"], dev)
+        self.text_pos = _f(sd["text_pos_embedding.emb.weight"], dev)
+        self.w_head = _bf(sd["mel_head.weight"], dev)
+        self.b_head = _f(sd["mel_head.bias"], dev)
+
+
+class AREngine:
+    def __init__(self, sd, cfg: ModelConfig, device="cuda"):
+        self.cfg = cfg
+        self.dev = torch.device(device)
+        self.w = ARWeights(sd, cfg, self.dev)
+        self.D = cfg.ar_dim
+        self.H = cfg.ar_heads
+        self.V = cfg.number_mel_codes
+        self._dec = None  # decode workspace keyed by (B, P, Nmax)
+
+    # ------------------------------------------------------------------ shared trunk over M tokens
+    def _alloc_trunk(self, M):
+        D, dev = self.D, self.dev
+        return dict(a=torch.empty(M, D, dtype=torch.bfloat16, device=dev),
+                    qkv=torch.empty(M, 3 * D, dtype=torch.bfloat16, device=dev),
+                    o=torch.empty(M, D, dtype=torch.bfloat16, device=dev),
+                    h=torch.empty(M, 4 * D, dtype=torch.bfloat16, device=dev))
+
+    def _layer(self, lw, x, M, ws, attn_fn):
+        D = self.D
+        lib.layernorm(x, M, D, lw["ln1_g"], lw["ln1_b"], out_bf16=ws["a"])
+        lib.gemm(ws["a"], lw["wqkv"], M=M, N=3 * D, K=D, bias=lw["bqkv"], out_bf16=ws["qkv"])
+        attn_fn(ws["qkv"], ws["o"])
+        lib.gemm(ws["o"], lw["wproj"], M=M, N=D, K=D, bias=lw["bproj"], residual=x, out_f32=x)
+        lib.layernorm(x, M, D, lw["ln2_g"], lw["ln2_b"], out_bf16=ws["a"])
+        lib.gemm(ws["a"], lw["wfc"], M=M, N=4 * D, K=D, bias=lw["bfc"], act=lib.ACT_GELU_NEW, out_bf16=ws["h"])
+        lib.gemm(ws["h"], lw["wproj2"], M=M, N=D, K=4 * D, bias=lw["bproj2"], residual=x, out_f32=x)
+
+    def _prompt_ids(self, text_tokens):
+        cfg = self.cfg
+        t = [int(v) for v in text_tokens]
+        return [cfg.start_text_token] + t + [cfg.stop_text_token]   # autoregressive.py:538-539 (api.py:391 padded once)
+
+    # ------------------------------------------------------------------ prefill
+    def _prefill(self, cond_latent, text_tokens, st):
+        """Runs the prompt [cond | text(T+3) | start_mel] once (shared by every candidate), fills the prefix
+        KV cache and returns logits of the first sampling step [1, V]."""
+        cfg, D, H, dev = self.cfg, self.D, self.H, self.dev
+        ids = self._prompt_ids(text_tokens)
+        P = len(ids) + 2
+        assert P == st["P"]
+        x = st["px"]
+        # rows 1..P-2: text, row P-1: start mel token at mel position 0, row 0: conditioning latent
+        tid = torch.tensor(ids, dtype=torch.int32, device=dev)
+        tpos = torch.arange(len(ids), dtype=torch.int32, device=dev)
+        lib.embed(tid, tpos, len(ids), D, self.w.text_emb, self.w.text_pos, x[1:])
+        sid = torch.tensor([cfg.start_mel_token], dtype=torch.int32, device=dev)
+        spos = torch.zeros(1, dtype=torch.int32, device=dev)
+        lib.embed(sid, spos, 1, D, self.w.mel_emb, self.w.mel_pos, x[P - 1:])
+        x[0].copy_(cond_latent.reshape(-1).to(device=dev, dtype=torch.float32))
+        ws = st["pws"]
+        for l, lw in enumerate(self.w.layers):
+            def attn(qkv, o, l=l):
+                lib.ar_store_prefix(qkv, P, H, st["pk"][l], st["pv"][l])
+                lib.attention(qkv, o, nseq=1, T=P, H=H, ld=3 * D, ldo=D, k_off=D, v_off=2 * D, scale=0.125, causal=True)
+            self._layer(lw, x, P, ws, attn)
+        lib.layernorm(x[P - 1:], 1, D, self.w.lnf_g, self.w.lnf_b, self.w.fn_g, self.w.fn_b, out_bf16=st["hn"][:1])
+        lib.gemm(st["hn"], self.w.w_head, M=1, N=self.V, K=D, bias=self.w.b_head, out_f32=st["logits"])
+
+    # ------------------------------------------------------------------ decode workspace + graph
+    def _decode_state(self, B, P, Nmax):
+        key = (B, P, Nmax)
+        if self._dec is not None and self._dec["key"] == key:
+            return self._dec
+        cfg, D, H, dev = self.cfg, self.D, self.H, self.dev
+        L = cfg.ar_layers
+        st = dict(key=key, P=P, B=B, Nmax=Nmax)
+        st["px"] = torch.empty(P, D, dtype=torch.float32, device=dev)
+        st["pws"] = self._alloc_trunk(P)
+        st["pk"] = torch.empty(L, H, P, 64, dtype=torch.bfloat16, device=dev)
+        st["pv"] = torch.empty(L, H, P, 64, dtype=torch.bfloat16, device=dev)
+        st["ck"] = torch.zeros(L, B, H, Nmax, 64, dtype=torch.bfloat16, device=dev)
+        st["cv"] = torch.zeros(L, B, H, Nmax, 64, dtype=torch.bfloat16, device=dev)
+        st["x"] = torch.empty(B, D, dtype=torch.float32, device=dev)
+        st["ws"] = self._alloc_trunk(B)
+        st["hn"] = torch.empty(max(B, 1), D, dtype=torch.bfloat16, device=dev)
+        st["logits"] = torch.empty(B, self.V, dtype=torch.float32, device=dev)
+        st["state"] = torch.zeros(64, dtype=torch.int32, device=dev)
+        st["codes"] = torch.empty(B, Nmax, dtype=torch.int32, device=dev)
+        st["seen"] = torch.zeros(B, (self.V + 31) // 32, dtype=torch.int32, device=dev)
+        st["finished"] = torch.zeros(B, dtype=torch.int32, device=dev)
+        st["uniforms"] = torch.empty(B, Nmax, dtype=torch.float32, device=dev)
+        st["graph"] = None
+        st["graph_params"] = None
+        self._dec = st
+        return st
+
+    def _decode_step(self, st, sp):
+        """One trunk pass for the last sampled token of every candidate + fused sampling of the next one."""
+        B, P, Nmax, D, H = st["B"], st["P"], st["Nmax"], self.D, self.H
+        x, ws = st["x"], st["ws"]
+        lib.ar_embed_step(st["codes"], Nmax, st["state"], self.w.mel_emb, self.w.mel_pos, B, D, sp["pos_mode"], x)
+        for l, lw in enumerate(self.w.layers):
+            def attn(qkv, o, l=l):
+                lib.ar_decode_attention(qkv, st["pk"][l], st["pv"][l], st["ck"][l], st["cv"][l], st["state"], B, H, P,
+                                        Nmax, o)
+            self._layer(lw, x, B, ws, attn)
+        lib.layernorm(x, B, D, self.w.lnf_g, self.w.lnf_b, self.w.fn_g, self.w.fn_b, out_bf16=st["hn"])
+        lib.gemm(st["hn"], self.w.w_head, M=B, N=self.V, K=D, bias=self.w.b_head, out_f32=st["logits"])
+        lib.ar_sample(st["logits"], self.V, self.V, B, st["uniforms"], Nmax, st["seen"], st["codes"], Nmax,
+                      st["finished"], st["state"], sp["temperature"], sp["top_k"], sp["top_p"], sp["rep_penalty"],
+                      self.cfg.stop_mel_token, advance=True)
+
+    def generate(self, cond_latent, text_tokens, num_candidates, max_new, uniforms=None, seed=None, temperature=0.8,
+                 top_k=50, top_p=0.8, repetition_penalty=2.0, pos_mode="ref_kv_quirk", use_graph=True,
+                 stop_check_every=32):
+        """≙ num_candidates/bs calls of UnifiedVoice.inference_speech (autoregressive.py:535-563), all candidates in
+        ONE batch with a shared-prefix KV cache. Returns int32 codes [num_candidates, max_new] padded with the
+        stop token (api.py:425-426). `uniforms` [B, max_new] injects the sampling randomness (parity mode)."""
+        cfg, dev = self.cfg, self.dev
+        B, Nmax = int(num_candidates), int(max_new)
+        P = len(text_tokens) + 4  # cond + [start, tokens(padded), stop] + start_mel
+        st = self._decode_state(B, P, Nmax)
+        sp = dict(temperature=float(temperature), top_k=int(top_k), top_p=float(top_p),
+                  rep_penalty=float(repetition_penalty), pos_mode=1 if pos_mode == "ref_kv_quirk" else 0)
+        if uniforms is None:
+            g = torch.Generator(device=dev)
+            g.manual_seed(0 if seed is None else int(seed))
+            st["uniforms"].copy_(torch.rand(B, Nmax, generator=g, device=dev))
+        else:
+            st["uniforms"].copy_(uniforms.to(device=dev, dtype=torch.float32))
+        st["state"].zero_()
+        st["finished"].zero_()
+        st["codes"].fill_(cfg.stop_mel_token)
+        st["seen"].zero_()
+        # HF's repetition penalty sees the fake prompt ids {1, start_mel} (autoregressive.py:546-548)
+        st["seen"][:, 0] = 2
+        w, bit = divmod(cfg.start_mel_token, 32)
+        st["seen"][:, w] |= (1 << bit) if bit < 31 else -(1 << 31)
+        self._prefill(cond_latent, text_tokens, st)
+        lib.ar_sample(st["logits"], 0, self.V, B, st["uniforms"], Nmax, st["seen"], st["codes"], Nmax, st["finished"],
+                      st["state"], sp["temperature"], sp["top_k"], sp["top_p"], sp["rep_penalty"], cfg.stop_mel_token,
+                      advance=True)
+        steps = Nmax - 1
+        if steps > 0:
+            if use_graph:
+                if st["graph"] is None or st["graph_params"] != sp:
+                    # warm-up once eagerly (module loading / attribute setting must not happen under capture),
+                    # then restore the sampler state and capture
+                    snap = {k: st[k].clone() for k in ("state", "codes", "seen", "finished")}
+                    self._decode_step(st, sp)
+                    torch.cuda.synchronize()
+                    for k, v in snap.items():
+                        st[k].copy_(v)
+                    g = torch.cuda.CUDAGraph()
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        with torch.cuda.graph(g, stream=side):
+                            self._decode_step(st, sp)
+                    torch.cuda.current_stream().wait_stream(side)
+                    for k, v in snap.items():
+                        st[k].copy_(v)
+                    st["graph"], st["graph_params"] = g, dict(sp)
+                done = 0
+                while done < steps:
+                    n = min(stop_check_every, steps - done)
+                    for _ in range(n):
+                        st["graph"].replay()
+                    done += n
+                    if done < steps and int(st["state"][1].item()) == 1:
+                        break
+            else:
+                for i in range(steps):
+                    self._decode_step(st, sp)
+        return st["codes"].clone()
+
+    # ------------------------------------------------------------------ teacher-forced passes
+    def _forward_sequences(self, emb_fn, nseq, T):
+        """Runs the trunk over nseq sequences of T tokens (causal). emb_fn fills x [nseq*T, D]. Returns x."""
+        D, H = self.D, self.H
+        M = nseq * T
+        x = torch.empty(M, D, dtype=torch.float32, device=self.dev)
+        emb_fn(x)
+        ws = self._alloc_trunk(M)
+
+        def attn(qkv, o):
+            lib.attention(qkv, o, nseq=nseq, T=T, H=H, ld=3 * D, ldo=D, k_off=D, v_off=2 * D, scale=0.125, causal=True)
+        for lw in self.w.layers:
+            self._layer(lw, x, M, ws, attn)
+        return x
+
+    def teacher_forced_logits(self, cond_latent, text_tokens, codes, pos_mode="ref_kv_quirk"):
+        """Logits at every decode position when fed `codes` [B, n] (parity check of rows a1/a2)."""
+        cfg, D, dev = self.cfg, self.D, self.dev
+        B, n = codes.shape
+        ids = self._prompt_ids(text_tokens)
+        Pm = len(ids) + 1            # cond + text
+        T = Pm + n + 1
+        quirk = pos_mode == "ref_kv_quirk"
+
+        def emb(x):
+            xv = x.view(B, T, D)
+            tid = torch.tensor(ids, dtype=torch.int32, device=dev)
+            tpos = torch.arange(len(ids), dtype=torch.int32, device=dev)
+            tmp = torch.empty(len(ids), D, dtype=torch.float32, device=dev)
+            lib.embed(tid, tpos, len(ids), D, self.w.text_emb, self.w.text_pos, tmp)
+            xv[:, 0] = cond_latent.reshape(-1).to(dev)
+            xv[:, 1:Pm] = tmp
+            mid = torch.cat([torch.full((B, 1), cfg.start_mel_token, dtype=torch.int32, device=dev),
+                             codes.to(device=dev, dtype=torch.int32)], dim=1).contiguous()
+            mpos = torch.tensor([(j + 1 if (quirk and j >= 1) else j) for j in range(n + 1)], dtype=torch.int32,
+                                device=dev).repeat(B, 1).contiguous()
+            tmp2 = torch.empty(B * (n + 1), D, dtype=torch.float32, device=dev)
+            lib.embed(mid.view(-1), mpos.view(-1), B * (n + 1), D, self.w.mel_emb, self.w.mel_pos, tmp2)
+            xv[:, Pm:] = tmp2.view(B, n + 1, D)
+        x = self._forward_sequences(emb, B, T)
+        M = B * T
+        hn = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
+        lib.layernorm(x, M, D, self.w.lnf_g, self.w.lnf_b, self.w.fn_g, self.w.fn_b, out_bf16=hn)
+        logits = torch.empty(M, self.V, dtype=torch.float32, device=dev)
+        lib.gemm(hn, self.w.w_head, M=M, N=self.V, K=D, bias=self.w.b_head, out_f32=logits)
+        return logits.view(B, T, self.V)[:, Pm:]
+
+    def latents(self, cond_latent, text_tokens, codes):
+        """≙ UnifiedVoice.forward(..., return_latent=True, clip_inputs=False) (autoregressive.py:454-512, called at
+        api.py:521-524). codes [k, L] -> fp32 [k, L, D]."""
+        cfg, D, dev = self.cfg, self.D, self.dev
+        k, L = codes.shape
+        ids = self._prompt_ids(text_tokens)
+        Pm = len(ids) + 1
+        T = Pm + L + 2
+
+        def emb(x):
+            xv = x.view(k, T, D)
+            tid = torch.tensor(ids, dtype=torch.int32, device=dev)
+            tpos = torch.arange(len(ids), dtype=torch.int32, device=dev)
+            tmp = torch.empty(len(ids), D, dtype=torch.float32, device=dev)
+            lib.embed(tid, tpos, len(ids), D, self.w.text_emb, self.w.text_pos, tmp)
+            xv[:, 0] = cond_latent.reshape(-1).to(dev)
+            xv[:, 1:Pm] = tmp
+            mid = torch.cat([torch.full((k, 1), cfg.start_mel_token, dtype=torch.int32, device=dev),
+                             codes.to(device=dev, dtype=torch.int32),
+                             torch.full((k, 1), cfg.stop_mel_token, dtype=torch.int32, device=dev)], dim=1).contiguous()
+            mpos = torch.arange(L + 2, dtype=torch.int32, device=dev).repeat(k, 1).contiguous()
+            tmp2 = torch.empty(k * (L + 2), D, dtype=torch.float32, device=dev)
+            lib.embed(mid.view(-1), mpos.view(-1), k * (L + 2), D, self.w.mel_emb, self.w.mel_pos, tmp2)
+            xv[:, Pm:] = tmp2.view(k, L + 2, D)
+        x = self._forward_sequences(emb, k, T)
+        M = k * T
+        out = torch.empty(M, D, dtype=torch.float32, device=dev)
+        lib.layernorm(x, M, D, self.w.lnf_g, self.w.lnf_b, self.w.fn_g, self.w.fn_b, out_f32=out)
+        return out.view(k, T, D)[:, Pm:Pm + L].contiguous()

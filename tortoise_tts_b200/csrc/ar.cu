@@ -1,0 +1,239 @@
+// Autoregressive sampler support kernels (UnifiedVoice / GPT2InferenceModel hot loop):
+// embedding gathers, the fused HF sample() step and the post-processing of generated codes.
+#include "common.cuh"
+#include "ttb_internal.h"
+
+namespace ttb {
+
+__global__ void embed_kernel(const int* __restrict__ ids, const int* __restrict__ pos, int n, int D,
+                             const float* __restrict__ table, const float* __restrict__ pos_table,
+                             float* __restrict__ out) {
+  const int r = blockIdx.x;
+  const float* t = table + (long long)ids[r] * D;
+  const float* p = (pos_table && pos) ? pos_table + (long long)pos[r] * D : nullptr;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) out[(long long)r * D + c] = t[c] + (p ? p[c] : 0.f);
+}
+
+__global__ void ar_embed_step_kernel(const int* __restrict__ codes, int ld_codes, const TtbArState* __restrict__ state,
+                                     const float* __restrict__ mel_emb, const float* __restrict__ mel_pos, int D,
+                                     int pos_mode, float* __restrict__ x) {
+  const int b = blockIdx.x;
+  const int j = state->step;                 // index of this token inside the mel segment (start token = 0)
+  const int tok = codes[(long long)b * ld_codes + j - 1];
+  const int pos = pos_mode ? j + 1 : j;      // autoregressive.py:147-149
+  const float* t = mel_emb + (long long)tok * D;
+  const float* p = mel_pos + (long long)pos * D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) x[(long long)b * D + c] = t[c] + p[c];
+}
+
+// ------------------------------------------------------------------ fused sampler
+// One block (256 threads) per candidate. Radix-select of the top_k-th largest value (4 passes of 8 bits over the
+// order-preserving uint32 image of the float), gather of the survivors (<= CAP), bitonic sort by one warp,
+// softmax, top-p cut on the exclusive prefix mass, inverse-CDF draw.
+constexpr int SAMP_THREADS = 256;
+constexpr int SAMP_CAP = 64;
+
+TTB_DEVINL uint32_t f2key(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(SAMP_THREADS)
+ar_sample_kernel(const float* __restrict__ logits, int ld_logits, int V, const float* __restrict__ uniforms, int ld_u,
+                 uint32_t* __restrict__ seen, int* __restrict__ codes, int ld_codes, int* __restrict__ finished,
+                 const TtbArState* __restrict__ state, float temperature, int top_k, float top_p, float rep_penalty,
+                 int stop_token) {
+  extern __shared__ float sval[];           // V floats: processed scores
+  __shared__ int hist[256];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_remaining;
+  __shared__ float cand_v[SAMP_CAP];
+  __shared__ int cand_i[SAMP_CAP];
+  __shared__ int s_ncand;
+  const int b = blockIdx.x;
+  const int step = state->step;
+  const int words = (V + 31) >> 5;
+  uint32_t* myseen = seen + (long long)b * words;
+  const float* lrow = logits + (long long)b * ld_logits;
+  if (finished[b]) {
+    // HF: finished rows keep emitting pad_token_id (= stop token) (stream_generator.py:974-981)
+    if (threadIdx.x == 0) codes[(long long)b * ld_codes + step] = stop_token;
+    return;
+  }
+  for (int i = threadIdx.x; i < V; i += SAMP_THREADS) {
+    float s = lrow[i];
+    if ((myseen[i >> 5] >> (i & 31)) & 1u) s = (s < 0.f) ? s * rep_penalty : s / rep_penalty;
+    sval[i] = s / temperature;
+  }
+  if (threadIdx.x == 0) { s_prefix = 0; s_remaining = min(top_k, V); s_ncand = 0; }
+  __syncthreads();
+  // radix select: find key T of the k-th largest element
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+    const uint32_t mask = (pass == 0) ? 0u : (0xFFFFFFFFu << (shift + 8));
+    for (int i = threadIdx.x; i < V; i += SAMP_THREADS) {
+      const uint32_t k = f2key(sval[i]);
+      if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int rem = s_remaining;
+      int d = 255;
+      for (; d > 0; --d) {
+        if (hist[d] >= rem) break;
+        rem -= hist[d];
+      }
+      s_prefix = prefix | ((uint32_t)d << shift);
+      s_remaining = rem;
+    }
+    __syncthreads();
+  }
+  const uint32_t thr = s_prefix;  // key of the k-th largest; HF keeps everything >= it (ties included)
+  for (int i = threadIdx.x; i < V; i += SAMP_THREADS) {
+    const float s = sval[i];
+    if (f2key(s) >= thr) {
+      const int slot = atomicAdd(&s_ncand, 1);
+      if (slot < SAMP_CAP) { cand_v[slot] = s; cand_i[slot] = i; }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const int n = min(s_ncand, SAMP_CAP);
+    // two elements per lane; bitonic sort of 64, descending by value then ascending by index
+    float v0 = (lane < n) ? cand_v[lane] : -INFINITY, v1 = (lane + 32 < n) ? cand_v[lane + 32] : -INFINITY;
+    int i0 = (lane < n) ? cand_i[lane] : 0x7fffffff, i1 = (lane + 32 < n) ? cand_i[lane + 32] : 0x7fffffff;
+    __syncwarp();
+    cand_v[lane] = v0; cand_v[lane + 32] = v1; cand_i[lane] = i0; cand_i[lane + 32] = i1;
+    __syncwarp();
+    for (int k = 2; k <= 64; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int e = lane; e < 64; e += 32) {
+          const int partner = e ^ j;
+          if (partner > e) {
+            const bool desc = ((e & k) == 0);
+            const float a = cand_v[e], c = cand_v[partner];
+            const int ia = cand_i[e], ic = cand_i[partner];
+            const bool a_before = (a > c) || (a == c && ia < ic);  // a should precede c in descending order
+            if (desc ? !a_before : a_before) {
+              cand_v[e] = c; cand_v[partner] = a; cand_i[e] = ic; cand_i[partner] = ia;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    // softmax over the survivors (descending), top-p on exclusive prefix mass
+    const float vmax = cand_v[0];
+    float p0 = (lane < n) ? __expf(cand_v[lane] - vmax) : 0.f;
+    float p1 = (lane + 32 < n) ? __expf(cand_v[lane + 32] - vmax) : 0.f;
+    const float tot = warp_sum(p0 + p1);
+    p0 /= tot; p1 /= tot;
+    // inclusive scan over 64 entries in order (lane, then lane+32)
+    float c0 = p0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { float t = __shfl_up_sync(0xffffffffu, c0, o); if (lane >= o) c0 += t; }
+    const float first_half = __shfl_sync(0xffffffffu, c0, 31);
+    float c1 = p1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { float t = __shfl_up_sync(0xffffffffu, c1, o); if (lane >= o) c1 += t; }
+    c1 += first_half;
+    const bool keep0 = (lane < n) && ((c0 - p0) < top_p || lane == 0);
+    const bool keep1 = (lane + 32 < n) && ((c1 - p1) < top_p);
+    const float kept = warp_sum((keep0 ? p0 : 0.f) + (keep1 ? p1 : 0.f));
+    // draw: smallest index with cumulative kept mass / kept > u (kept set is a prefix of the sorted list)
+    const float u = uniforms[(long long)b * ld_u + step] * kept;
+    const unsigned m0 = __ballot_sync(0xffffffffu, keep0 && c0 > u);
+    const unsigned m1 = __ballot_sync(0xffffffffu, keep1 && c1 > u);
+    const unsigned k0m = __ballot_sync(0xffffffffu, keep0);
+    const unsigned k1m = __ballot_sync(0xffffffffu, keep1);
+    int pick;
+    if (m0) pick = __ffs(m0) - 1;
+    else if (m1) pick = 32 + __ffs(m1) - 1;
+    else pick = k1m ? 32 + (31 - __clz(k1m)) : (31 - __clz(k0m));  // numerical slack: last kept
+    if (lane == 0) {
+      const int tok = cand_i[pick];
+      codes[(long long)b * ld_codes + step] = tok;
+      myseen[tok >> 5] |= (1u << (tok & 31));
+      if (tok == stop_token) finished[b] = 1;
+    }
+  }
+}
+
+__global__ void ar_sample_advance_kernel(TtbArState* state, const int* __restrict__ finished, int B) {
+  __shared__ int any_unfinished;
+  if (threadIdx.x == 0) any_unfinished = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < B; i += blockDim.x)
+    if (!finished[i]) any_unfinished = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    state->step += 1;
+    state->all_finished = any_unfinished ? 0 : 1;
+  }
+}
+
+// fix_autoregressive_output (api.py:87-114) + calm trim (api.py:547-556); one thread per row (rows are short)
+__global__ void ar_fix_codes_kernel(int* __restrict__ codes, int B, int L, int stop_token, int* __restrict__ trim_len) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int* c = codes + (long long)b * L;
+  int stm = -1;
+  for (int i = 0; i < L; ++i) if (c[i] == stop_token) { stm = i; break; }
+  if (stm >= 0) {
+    for (int i = stm; i < L; ++i) c[i] = 83;
+    if (L >= 3) { c[L - 3] = 45; c[L - 2] = 45; c[L - 1] = 248; }
+  }
+  int run = 0, cut = L;
+  for (int i = 0; i < L; ++i) {
+    run = (c[i] == 83) ? run + 1 : 0;
+    if (run > 8) { cut = i; break; }
+  }
+  if (trim_len) trim_len[b] = cut;
+}
+
+}  // namespace ttb
+using namespace ttb;
+
+extern "C" int ttb_embed(const int* ids, const int* pos, int n, int D, const float* table, const float* pos_table,
+                         float* out, void* stream) {
+  if (n <= 0) return 0;
+  embed_kernel<<<n, 256, 0, static_cast<cudaStream_t>(stream)>>>(ids, pos, n, D, table, pos_table, out);
+  TTB_CHECK_LAUNCH("embed_kernel");
+  return 0;
+}
+
+extern "C" int ttb_ar_embed_step(const int* codes, int ld_codes, const TtbArState* state, const float* mel_emb,
+                                 const float* mel_pos, int B, int D, int pos_mode, float* x, void* stream) {
+  ar_embed_step_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(codes, ld_codes, state, mel_emb, mel_pos, D,
+                                                                        pos_mode, x);
+  TTB_CHECK_LAUNCH("ar_embed_step_kernel");
+  return 0;
+}
+
+extern "C" int ttb_ar_sample(const float* logits, int ld_logits, int V, int B, const float* uniforms, int ld_u,
+                             uint32_t* seen, int* codes, int ld_codes, int* finished, TtbArState* state,
+                             float temperature, int top_k, float top_p, float rep_penalty, int stop_token, int advance,
+                             void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (top_k <= 0 || top_k > 50) { set_error("ttb_ar_sample: top_k=%d unsupported (1..50)", top_k); return -1; }
+  const size_t smem = (size_t)V * sizeof(float);
+  if (smem > 40 * 1024) { set_error("ttb_ar_sample: vocabulary %d too large", V); return -1; }
+  ar_sample_kernel<<<B, SAMP_THREADS, smem, st>>>(logits, ld_logits, V, uniforms, ld_u, seen, codes, ld_codes, finished,
+                                                  state, temperature, top_k, top_p, rep_penalty, stop_token);
+  TTB_CHECK_LAUNCH("ar_sample_kernel");
+  if (advance) {
+    ar_sample_advance_kernel<<<1, 256, 0, st>>>(state, finished, B);
+    TTB_CHECK_LAUNCH("ar_sample_advance_kernel");
+  }
+  return 0;
+}
+
+extern "C" int ttb_ar_fix_codes(int* codes, int B, int L, int stop_token, int* trim_len, void* stream) {
+  ar_fix_codes_kernel<<<(B + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(codes, B, L, stop_token, trim_len);
+  TTB_CHECK_LAUNCH("ar_fix_codes_kernel");
+  return 0;
+}

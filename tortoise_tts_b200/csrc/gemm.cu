@@ -1,0 +1,373 @@
+// tcgen05 GEMM / conv-as-GEMM for sm_100a.
+//
+//   D[b, m, n] = epilogue( sum_{tap, k} A[b, m + tap*1 - pad, k] * W[n, tap*K + k] )
+//
+// A: bf16 activations, token-major [batch, rows, K] (K contiguous), streamed by TMA (3-D map; out-of-range
+//    rows are zero-filled by the TMA unit, which is exactly Conv1d zero padding).
+// W: bf16 weights [N, taps*K] (K-major), streamed by TMA.
+// Accumulator: fp32 in TMEM (128 lanes x BN columns), written by tcgen05.mma (UMMA 128xBNx16, cta_group::1).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2..5 = epilogue
+// (tcgen05.ld 32x32b -> bias / activation / residual -> global).
+//
+// Replaces, behind the C-ABI, every dense contraction of the reference hot path that PyTorch dispatches to
+// cuBLAS / cuDNN: HF Conv1D addmm (GPT-2 c_attn/c_proj/c_fc, via autoregressive.py:150-163), nn.Linear
+// (mel_head, CLVP to_q/k/v/out/FF xtransformers.py:519-521,440-474), nn.Conv1d k=1/k=3 of DiffusionTts
+// (diffusion_decoder.py:83-103, arch_util.py:107-111) and the UnivNet kernel-predictor convs (vocoder.py:40-64).
+#include "common.cuh"
+#include "ttb_internal.h"
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <cstring>
+
+namespace ttb {
+
+// ------------------------------------------------------------------ tensor-map cache (host)
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  uint64_t d0, d1, d2, s1, s2;
+  uint32_t b0, b1;
+  bool operator<(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) < 0; }
+};
+
+// bf16, up to 3 dims (dim0 contiguous), box = {b0, b1, 1}, SWIZZLE_128B (b0 * 2 bytes must be 128)
+int get_tensor_map_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
+                        uint64_t stride2_elems, uint32_t b0, uint32_t b1) {
+  static std::map<MapKey, CUtensorMap> cache;
+  static std::mutex mu;
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.d0 = d0; key.d1 = d1; key.d2 = d2; key.s1 = stride1_elems; key.s2 = stride2_elems;
+  key.b0 = b0; key.b1 = b1;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return 0; }
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return -1; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((stride1_elems * 2) & 15) || ((stride2_elems * 2) & 15)) {
+    set_error("tensor map: pointer/strides must be 16-byte aligned (ptr=%p s1=%llu s2=%llu)", ptr,
+              (unsigned long long)stride1_elems, (unsigned long long)stride2_elems);
+    return -1;
+  }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_elems * 2, stride2_elems * 2};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): dims=%llu,%llu,%llu strides=%llu,%llu box=%u,%u", (int)r,
+              (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+              (unsigned long long)strides[0], (unsigned long long)strides[1], b0, b1);
+    return -1;
+  }
+  cache[key] = m;
+  *out = m;
+  return 0;
+}
+
+// ------------------------------------------------------------------ kernel
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmEpilogue {
+  const float* bias;       // [N] or null
+  const float* residual;   // fp32 [batch, M, ldr] or null (added after activation)
+  float* out_f32;          // [batch, M, ldo] or null
+  __nv_bfloat16* out_bf16; // [batch, M, ldob] or null
+  long long res_bstride, outf_bstride, outb_bstride;
+  int ldr, ldo, ldob;
+  int act;                 // TTB_ACT_*
+  float alpha;             // scales the accumulator before bias
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
+                    int K, int taps, int pad, GemmEpilogue ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using L = GemmSmem<BN, STAGES>;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * BM;
+  const int bz = blockIdx.z;
+  const int kblocks_per_tap = K / BK;
+  const int num_kb = kblocks_per_tap * taps;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const int tap = kb / kblocks_per_tap;
+        const int kk = (kb - tap * kblocks_per_tap) * BK;
+        uint8_t* sa = smem + stage * L::STAGE_BYTES;
+        uint8_t* sb = sa + L::A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+        tma_load_3d(sa, &map_a, &full_bar[stage], kk, m0 + tap - pad, bz);
+        tma_load_3d(sb, &map_b, &full_bar[stage], tap * K + kk, n0, 0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+        const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t da = umma_desc_kmajor_sw128(sa + k * 32);
+          const uint64_t db = umma_desc_kmajor_sw128(sb + k * 32);
+          umma_bf16_ss(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(accum_bar);
+    }
+  } else {
+    // ===== epilogue: warps 2..5; warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const bool row_ok = m < M;
+    const float* res_row = ep.residual ? ep.residual + (long long)bz * ep.res_bstride + (long long)m * ep.ldr : nullptr;
+    float* of_row = ep.out_f32 ? ep.out_f32 + (long long)bz * ep.outf_bstride + (long long)m * ep.ldo : nullptr;
+    __nv_bfloat16* ob_row = ep.out_bf16 ? ep.out_bf16 + (long long)bz * ep.outb_bstride + (long long)m * ep.ldob : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+      tmem_ld_wait();
+      const int nb = n0 + c;
+      if (!row_ok || nb >= N) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(r[j]) * ep.alpha;
+        if (ep.bias && nb + j < N) x += __ldg(ep.bias + nb + j);
+        v[j] = x;
+      }
+      if (ep.act == TTB_ACT_GEGLU) {
+        // columns interleaved (u0,g0,u1,g1,...): out[j] = u * gelu_erf(g); output width N/2
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf(v[2 * j + 1]);
+        const int ob = nb >> 1;
+        if (ob_row) {
+          if (nb + 32 <= N) {
+            uint4* dst = reinterpret_cast<uint4*>(ob_row + ob);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              dst[j] = make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
+                                  pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
+          } else {
+            for (int j = 0; j < 16 && nb + 2 * j < N; ++j) ob_row[ob + j] = __float2bfloat16(o[j]);
+          }
+        }
+        if (of_row) for (int j = 0; j < 16 && nb + 2 * j < N; ++j) of_row[ob + j] = o[j];
+        continue;
+      }
+      if (ep.act == TTB_ACT_GELU_NEW) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_new(v[j]);
+      } else if (ep.act == TTB_ACT_SILU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
+      } else if (ep.act == TTB_ACT_LRELU02) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = leaky(v[j], 0.2f);
+      }
+      const bool full = (nb + 32 <= N);
+      if (res_row) {
+        if (full && ((ep.ldr & 3) == 0)) {
+          const float4* rp = reinterpret_cast<const float4*>(res_row + nb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 t = rp[j];
+            v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+          }
+        } else {
+          for (int j = 0; j < 32 && nb + j < N; ++j) v[j] += res_row[nb + j];
+        }
+      }
+      if (of_row) {
+        if (full && ((ep.ldo & 3) == 0)) {
+          float4* dst = reinterpret_cast<float4*>(of_row + nb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          for (int j = 0; j < 32 && nb + j < N; ++j) of_row[nb + j] = v[j];
+        }
+      }
+      if (ob_row) {
+        if (full && ((ep.ldob & 7) == 0)) {
+          uint4* dst = reinterpret_cast<uint4*>(ob_row + nb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+        } else {
+          for (int j = 0; j < 32 && nb + j < N; ++j) ob_row[nb + j] = __float2bfloat16(v[j]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------ reference (SIMT) GEMM: test/bring-up checker
+__global__ void gemm_ref_kernel(const __nv_bfloat16* A, long long a_bstride, int lda, int rows, const __nv_bfloat16* W,
+                                int M, int N, int K, int taps, int pad, GemmEpilogue ep) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  const int bz = blockIdx.z;
+  if (n >= N || m >= M) return;
+  const int nn = (ep.act == TTB_ACT_GEGLU) ? (n & ~1) : n;
+  float acc[2] = {0.f, 0.f};
+  const int cnt = (ep.act == TTB_ACT_GEGLU) ? 2 : 1;
+  if (ep.act == TTB_ACT_GEGLU && (n & 1)) return;
+  for (int c = 0; c < cnt; ++c) {
+    float s = 0.f;
+    for (int tap = 0; tap < taps; ++tap) {
+      const int r = m + tap - pad;
+      if (r < 0 || r >= rows) continue;
+      const __nv_bfloat16* a = A + (long long)bz * a_bstride + (long long)r * lda;
+      const __nv_bfloat16* w = W + (long long)(nn + c) * taps * K + (long long)tap * K;
+      for (int k = 0; k < K; ++k) s += __bfloat162float(a[k]) * __bfloat162float(w[k]);
+    }
+    s *= ep.alpha;
+    if (ep.bias) s += ep.bias[nn + c];
+    acc[c] = s;
+  }
+  float v;
+  int on = n;
+  if (ep.act == TTB_ACT_GEGLU) { v = acc[0] * gelu_erf(acc[1]); on = n >> 1; }
+  else {
+    v = acc[0];
+    if (ep.act == TTB_ACT_GELU_NEW) v = gelu_new(v);
+    else if (ep.act == TTB_ACT_SILU) v = silu(v);
+    else if (ep.act == TTB_ACT_LRELU02) v = leaky(v, 0.2f);
+    if (ep.residual) v += ep.residual[(long long)bz * ep.res_bstride + (long long)m * ep.ldr + n];
+  }
+  if (ep.out_f32) ep.out_f32[(long long)bz * ep.outf_bstride + (long long)m * ep.ldo + on] = v;
+  if (ep.out_bf16) ep.out_bf16[(long long)bz * ep.outb_bstride + (long long)m * ep.ldob + on] = __float2bfloat16(v);
+}
+
+static int g_gemm_impl = -1;  // 0 = tcgen05, 1 = SIMT reference (bring-up only; TTB_GEMM_IMPL=ref)
+
+template <int BN, int STAGES>
+static int launch_tc(const TtbGemmArgs& g, const GemmEpilogue& ep, cudaStream_t st) {
+  CUtensorMap ma, mb;
+  if (get_tensor_map_bf16(&ma, g.A, (uint64_t)g.K, (uint64_t)g.rows, (uint64_t)g.batch, (uint64_t)g.lda,
+                          (uint64_t)g.a_bstride, BK, BM)) return -1;
+  if (get_tensor_map_bf16(&mb, g.W, (uint64_t)g.K * g.taps, (uint64_t)g.N, 1, (uint64_t)g.K * g.taps,
+                          (uint64_t)g.K * g.taps * g.N, BK, BN)) return -1;
+  using L = GemmSmem<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm)");
+    attr_set = true;
+  }
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.batch);
+  gemm_bf16_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, st>>>(ma, mb, g.M, g.N, g.K, g.taps, g.pad, ep);
+  TTB_CHECK_LAUNCH("gemm_bf16_tc_kernel");
+  return 0;
+}
+
+}  // namespace ttb
+
+using namespace ttb;
+
+extern "C" int ttb_gemm(const TtbGemmArgs* gp, void* stream) {
+  const TtbGemmArgs& g = *gp;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g.K % BK != 0 || g.K <= 0) { set_error("ttb_gemm: K=%d must be a positive multiple of 64", g.K); return -1; }
+  if (g.taps < 1 || g.M <= 0 || g.N <= 0 || g.batch <= 0) { set_error("ttb_gemm: bad shape"); return -1; }
+  if (g.act == TTB_ACT_GEGLU && (g.N & 1)) { set_error("ttb_gemm: GEGLU needs even N"); return -1; }
+  GemmEpilogue ep;
+  ep.bias = g.bias; ep.residual = g.residual; ep.out_f32 = g.out_f32;
+  ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(g.out_bf16);
+  ep.res_bstride = g.res_bstride; ep.outf_bstride = g.outf_bstride; ep.outb_bstride = g.outb_bstride;
+  ep.ldr = g.ldr; ep.ldo = g.ldo; ep.ldob = g.ldob; ep.act = g.act; ep.alpha = g.alpha;
+  if (g_gemm_impl < 0) {
+    const char* e = getenv("TTB_GEMM_IMPL");
+    g_gemm_impl = (e && strcmp(e, "ref") == 0) ? 1 : 0;
+  }
+  if (g_gemm_impl == 1 || g.force_ref) {
+    dim3 block(128), grid((g.N + 127) / 128, g.M, g.batch);
+    gemm_ref_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g.A), g.a_bstride, g.lda, g.rows,
+                                            reinterpret_cast<const __nv_bfloat16*>(g.W), g.M, g.N, g.K, g.taps, g.pad, ep);
+    TTB_CHECK_LAUNCH("gemm_ref_kernel");
+    return 0;
+  }
+  // tile choice: fill the 148 SMs; small-N / small-M problems use narrower tiles
+  const long long tiles128 = (long long)((g.N + 127) / 128) * ((g.M + BM - 1) / BM) * g.batch;
+  if (g.tile_n == 64 || (g.tile_n == 0 && tiles128 < 148)) return launch_tc<64, 4>(g, ep, st);
+  return launch_tc<128, 3>(g, ep, st);
+}

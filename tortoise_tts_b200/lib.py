@@ -1,0 +1,247 @@
+"""ctypes binding of libttb.so (include/ttb.h). Thin: torch tensors in, raw pointers across the C-ABI.
+
+There is NO fallback: if the library is missing or a call fails, this module raises.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libttb.so")
+
+ACT_NONE, ACT_GELU_NEW, ACT_SILU, ACT_GEGLU, ACT_LRELU02 = 0, 1, 2, 3, 4
+
+
+class TtbError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("W", C.c_void_p), ("bias", C.c_void_p), ("residual", C.c_void_p),
+                ("out_f32", C.c_void_p), ("out_bf16", C.c_void_p),
+                ("a_bstride", C.c_longlong), ("res_bstride", C.c_longlong), ("outf_bstride", C.c_longlong),
+                ("outb_bstride", C.c_longlong),
+                ("lda", C.c_int), ("ldr", C.c_int), ("ldo", C.c_int), ("ldob", C.c_int),
+                ("rows", C.c_int), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+                ("taps", C.c_int), ("pad", C.c_int), ("batch", C.c_int), ("act", C.c_int),
+                ("alpha", C.c_float), ("tile_n", C.c_int), ("force_ref", C.c_int)]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [("qkv", C.c_void_p), ("out", C.c_void_p), ("bias", C.c_void_p),
+                ("nseq", C.c_int), ("T", C.c_int), ("H", C.c_int),
+                ("ld", C.c_int), ("ldo", C.c_int), ("k_off", C.c_int), ("v_off", C.c_int),
+                ("scale", C.c_float), ("causal", C.c_int)]
+
+
+class DiffStepArgs(C.Structure):
+    _fields_ = [("model_out", C.c_void_p), ("out_bstride", C.c_longlong), ("ld_out", C.c_int),
+                ("x", C.c_void_p), ("x_bf16", C.c_void_p), ("ld_xb", C.c_int),
+                ("noise", C.c_void_p), ("tables", C.c_void_p), ("step", C.c_void_p),
+                ("S", C.c_int), ("C", C.c_int), ("iters", C.c_int),
+                ("cond_free", C.c_int), ("cond_free_k", C.c_float), ("mel_out", C.c_void_p)]
+
+
+_lib = None
+
+# every symbol include/ttb.h declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = [
+    "ttb_last_error", "ttb_version", "ttb_device_ok", "ttb_gemm", "ttb_layernorm", "ttb_rmsnorm", "ttb_groupnorm",
+    "ttb_attention", "ttb_ar_embed_step", "ttb_ar_decode_attention", "ttb_ar_store_prefix", "ttb_ar_sample",
+    "ttb_ar_fix_codes", "ttb_embed", "ttb_clvp_rotary", "ttb_clvp_pool", "ttb_clvp_project",
+    "ttb_timestep_embedding", "ttb_linear_small", "ttb_interp_nearest", "ttb_diffusion_step", "ttb_counter_add",
+    "ttb_transpose_f32", "ttb_cast_pad_bf16", "ttb_broadcast_rows", "ttb_voc_conv1d", "ttb_voc_convt",
+    "ttb_voc_lvc_gate", "ttb_voc_to_tokens_bf16",
+]
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TtbError("libttb.so not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(no CPU/PyTorch fallback exists for the hot path)")
+    lib = C.CDLL(LIB_PATH)
+    lib.ttb_last_error.restype = C.c_char_p
+    for s in SYMBOLS:
+        if s != "ttb_last_error":
+            getattr(lib, s).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def _chk(rc, what):
+    if rc != 0:
+        raise TtbError("%s failed (%d): %s" % (what, rc, load().ttb_last_error().decode()))
+
+
+def _p(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _bf(t):
+    assert t is None or t.dtype == torch.bfloat16, t.dtype
+    return t
+
+
+def _f32(t):
+    assert t is None or t.dtype == torch.float32, t.dtype
+    return t
+
+
+# ------------------------------------------------------------------ wrappers
+def gemm(A, W, *, M, N, K, bias=None, residual=None, out_f32=None, out_bf16=None, lda=None, rows=None, batch=1,
+         a_bstride=0, res_bstride=0, outf_bstride=0, outb_bstride=0, ldr=None, ldo=None, ldob=None, taps=1, pad=0,
+         act=ACT_NONE, alpha=1.0, tile_n=0, force_ref=False):
+    """See include/ttb.h ttb_gemm. A: bf16 [batch, rows, lda]; W: bf16 [N, taps*K]."""
+    _bf(A), _bf(W), _f32(bias), _f32(residual), _f32(out_f32), _bf(out_bf16)
+    n_out = N // 2 if act == ACT_GEGLU else N
+    g = GemmArgs()
+    g.A, g.W, g.bias, g.residual = A.data_ptr(), W.data_ptr(), _p(bias).value or 0, _p(residual).value or 0
+    g.out_f32, g.out_bf16 = _p(out_f32).value or 0, _p(out_bf16).value or 0
+    g.a_bstride, g.res_bstride, g.outf_bstride, g.outb_bstride = a_bstride, res_bstride, outf_bstride, outb_bstride
+    g.lda = K if lda is None else lda
+    g.ldr = n_out if ldr is None else ldr
+    g.ldo = n_out if ldo is None else ldo
+    g.ldob = n_out if ldob is None else ldob
+    g.rows = M if rows is None else rows
+    g.M, g.N, g.K, g.taps, g.pad, g.batch, g.act = M, N, K, taps, pad, batch, act
+    g.alpha, g.tile_n, g.force_ref = alpha, tile_n, 1 if force_ref else 0
+    _chk(load().ttb_gemm(C.byref(g), _stream()), "ttb_gemm")
+
+
+def layernorm(x, M, D, g1, b1, g2=None, b2=None, out_bf16=None, out_f32=None):
+    _chk(load().ttb_layernorm(_p(_f32(x)), M, D, _p(g1), _p(b1), _p(g2), _p(b2), _p(_bf(out_bf16)), _p(_f32(out_f32)),
+                              _stream()), "ttb_layernorm")
+
+
+def rmsnorm(x, M, D, g, out_bf16):
+    _chk(load().ttb_rmsnorm(_p(_f32(x)), M, D, _p(g), _p(_bf(out_bf16)), _stream()), "ttb_rmsnorm")
+
+
+def groupnorm(x, B, S, Cc, groups, gamma, beta, partials, scale_shift=None, ss_bstride=0, ss_row=None, ss_row_stride=0,
+              silu=False, out_bf16=None, ldo=0, out_f32=None, ldof=0):
+    _chk(load().ttb_groupnorm(_p(_f32(x)), B, S, Cc, groups, _p(gamma), _p(beta), _p(scale_shift), ss_bstride,
+                              _p(ss_row), ss_row_stride, 1 if silu else 0, _p(partials), _p(_bf(out_bf16)), ldo, _p(_f32(out_f32)), ldof,
+                              _stream()), "ttb_groupnorm")
+
+
+def attention(qkv, out, *, nseq, T, H, ld, ldo, k_off, v_off, scale, causal=False, bias=None):
+    a = AttnArgs()
+    a.qkv, a.out, a.bias = _bf(qkv).data_ptr(), _bf(out).data_ptr(), _p(_f32(bias)).value or 0
+    a.nseq, a.T, a.H, a.ld, a.ldo, a.k_off, a.v_off = nseq, T, H, ld, ldo, k_off, v_off
+    a.scale, a.causal = scale, 1 if causal else 0
+    _chk(load().ttb_attention(C.byref(a), _stream()), "ttb_attention")
+
+
+def ar_embed_step(codes, ld_codes, state, mel_emb, mel_pos, B, D, pos_mode, x):
+    _chk(load().ttb_ar_embed_step(_p(codes), ld_codes, _p(state), _p(mel_emb), _p(mel_pos), B, D, pos_mode, _p(x),
+                                  _stream()), "ttb_ar_embed_step")
+
+
+def ar_decode_attention(qkv, pk, pv, ck, cv, state, B, H, P, Nmax, out):
+    _chk(load().ttb_ar_decode_attention(_p(_bf(qkv)), _p(_bf(pk)), _p(_bf(pv)), _p(_bf(ck)), _p(_bf(cv)), _p(state),
+                                        B, H, P, Nmax, _p(_bf(out)), _stream()), "ttb_ar_decode_attention")
+
+
+def ar_store_prefix(qkv, P, H, pk, pv):
+    _chk(load().ttb_ar_store_prefix(_p(_bf(qkv)), P, H, _p(_bf(pk)), _p(_bf(pv)), _stream()), "ttb_ar_store_prefix")
+
+
+def ar_sample(logits, ld_logits, V, B, uniforms, ld_u, seen, codes, ld_codes, finished, state, temperature, top_k,
+              top_p, rep_penalty, stop_token, advance=True):
+    _chk(load().ttb_ar_sample(_p(_f32(logits)), ld_logits, V, B, _p(_f32(uniforms)), ld_u, _p(seen), _p(codes), ld_codes,
+                              _p(finished), _p(state), C.c_float(temperature), top_k, C.c_float(top_p),
+                              C.c_float(rep_penalty), stop_token, 1 if advance else 0, _stream()), "ttb_ar_sample")
+
+
+def ar_fix_codes(codes, B, L, stop_token, trim_len):
+    _chk(load().ttb_ar_fix_codes(_p(codes), B, L, stop_token, _p(trim_len), _stream()), "ttb_ar_fix_codes")
+
+
+def embed(ids, pos, n, D, table, pos_table, out):
+    _chk(load().ttb_embed(_p(ids), _p(pos), n, D, _p(_f32(table)), _p(_f32(pos_table)), _p(_f32(out)), _stream()),
+         "ttb_embed")
+
+
+def clvp_rotary(qkv, nseq, T, H):
+    _chk(load().ttb_clvp_rotary(_p(_bf(qkv)), nseq, T, H, _stream()), "ttb_clvp_rotary")
+
+
+def clvp_pool(x, nseq, T, D, g, b, out):
+    _chk(load().ttb_clvp_pool(_p(_f32(x)), nseq, T, D, _p(g), _p(b), _p(_f32(out)), _stream()), "ttb_clvp_pool")
+
+
+def clvp_project(pooled, n, D, W, latents, text_latent, temp_exp, scores):
+    _chk(load().ttb_clvp_project(_p(_f32(pooled)), n, D, _p(_f32(W)), _p(latents), _p(text_latent),
+                                 C.c_float(temp_exp), _p(scores), _stream()), "ttb_clvp_project")
+
+
+def timestep_embedding(t, n, Cc, out):
+    _chk(load().ttb_timestep_embedding(_p(t), n, Cc, _p(_f32(out)), _stream()), "ttb_timestep_embedding")
+
+
+def linear_small(x, M, K, W, b, N, out, silu_in=False, silu_out=False):
+    _chk(load().ttb_linear_small(_p(_f32(x)), M, K, _p(_f32(W)), _p(b), N, 1 if silu_in else 0, 1 if silu_out else 0,
+                                 _p(_f32(out)), _stream()), "ttb_linear_small")
+
+
+def interp_nearest(x, N, S, Cc, out_bf16=None, ldo=0, out_f32=None, ldof=0):
+    _chk(load().ttb_interp_nearest(_p(_f32(x)), N, S, Cc, _p(_bf(out_bf16)), ldo, _p(_f32(out_f32)), ldof, _stream()),
+         "ttb_interp_nearest")
+
+
+def diffusion_step(model_out, out_bstride, ld_out, x, x_bf16, ld_xb, noise, tables, step, S, Cc, iters, cond_free,
+                   cond_free_k, mel_out=None):
+    a = DiffStepArgs()
+    a.model_out, a.out_bstride, a.ld_out = _f32(model_out).data_ptr(), out_bstride, ld_out
+    a.x, a.x_bf16, a.ld_xb = _f32(x).data_ptr(), _p(_bf(x_bf16)).value or 0, ld_xb
+    a.noise, a.tables, a.step = _f32(noise).data_ptr(), _f32(tables).data_ptr(), step.data_ptr()
+    a.S, a.C, a.iters, a.cond_free, a.cond_free_k = S, Cc, iters, 1 if cond_free else 0, cond_free_k
+    a.mel_out = _p(_f32(mel_out)).value or 0
+    _chk(load().ttb_diffusion_step(C.byref(a), _stream()), "ttb_diffusion_step")
+
+
+def counter_add(counter, delta):
+    _chk(load().ttb_counter_add(_p(counter), delta, _stream()), "ttb_counter_add")
+
+
+def transpose_f32(inp, R, Cc, out):
+    _chk(load().ttb_transpose_f32(_p(_f32(inp)), R, Cc, _p(_f32(out)), _stream()), "ttb_transpose_f32")
+
+
+def cast_pad_bf16(inp, R, Cc, ld_in, out, ldo, ncols_out=None):
+    _chk(load().ttb_cast_pad_bf16(_p(_f32(inp)), R, Cc, ld_in, _p(_bf(out)), ldo, ldo if ncols_out is None else ncols_out,
+                                  _stream()), "ttb_cast_pad_bf16")
+
+
+def broadcast_rows(row, R, Cc, out_f32, out_bf16, ldo):
+    _chk(load().ttb_broadcast_rows(_p(_f32(row)), R, Cc, _p(_f32(out_f32)), _p(_bf(out_bf16)), ldo, _stream()),
+         "ttb_broadcast_rows")
+
+
+def voc_conv1d(x, Cin, L, w, b, Cout, ksize, out, dilation=1, reflect=False, lrelu_in=1.0, lrelu_out=1.0,
+               tanh_out=False, residual=None):
+    _chk(load().ttb_voc_conv1d(_p(_f32(x)), Cin, L, _p(_f32(w)), _p(b), Cout, ksize, dilation, 1 if reflect else 0,
+                               C.c_float(lrelu_in), C.c_float(lrelu_out), 1 if tanh_out else 0, _p(residual),
+                               _p(_f32(out)), _stream()), "ttb_voc_conv1d")
+
+
+def voc_convt(x, Cc, L, w, b, stride, lrelu_in, out):
+    _chk(load().ttb_voc_convt(_p(_f32(x)), Cc, L, _p(_f32(w)), _p(b), stride, C.c_float(lrelu_in), _p(_f32(out)),
+                              _stream()), "ttb_voc_convt")
+
+
+def voc_lvc_gate(y, Cc, L, hop, kernels, ldk, koff, bias, ldb, boff, x):
+    _chk(load().ttb_voc_lvc_gate(_p(_f32(y)), Cc, L, hop, _p(_f32(kernels)), ldk, koff, _p(_f32(bias)), ldb, boff,
+                                 _p(_f32(x)), _stream()), "ttb_voc_lvc_gate")
+
+
+def voc_to_tokens_bf16(x, Cc, L, out, ldo):
+    _chk(load().ttb_voc_to_tokens_bf16(_p(_f32(x)), Cc, L, _p(_bf(out)), ldo, _stream()), "ttb_voc_to_tokens_bf16")
