@@ -1,0 +1,87 @@
+"""GPU: the tcgen05 GEMM / conv-as-GEMM (ttb_gemm) against a plain PyTorch fp32 reference of the same op on the
+same bf16-rounded operands (tolerance: fp32 accumulation-order noise, 2e-3 relative to the output scale), and the
+SIMT checker kernel against the same reference."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import report
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).cuda()
+
+
+def _run(M, N, K, taps=1, batch=1, act=0, bias=True, residual=False, out="f32", tile_n=0, force_ref=False, seed=0):
+    from tortoise_tts_b200 import lib
+    A = _mk((batch, M, K), 1.0, seed).to(torch.bfloat16)
+    W = _mk((N, taps, K), K ** -0.5, seed + 1).to(torch.bfloat16)
+    b = _mk((N,), 0.5, seed + 2) if bias else None
+    n_out = N // 2 if act == lib.ACT_GEGLU else N
+    res = _mk((batch, M, n_out), 1.0, seed + 3) if residual else None
+    of = torch.full((batch, M, n_out), float("nan"), device="cuda") if out in ("f32", "both") else None
+    ob = torch.zeros((batch, M, n_out), device="cuda", dtype=torch.bfloat16) if out in ("bf16", "both") else None
+    lib.gemm(A, W.reshape(N, taps * K), M=M, N=N, K=K, taps=taps, pad=(taps - 1) // 2, batch=batch, bias=b,
+             residual=res, out_f32=of, out_bf16=ob, a_bstride=M * K, res_bstride=M * n_out, outf_bstride=M * n_out,
+             outb_bstride=M * n_out, act=act, tile_n=tile_n, force_ref=force_ref)
+    torch.cuda.synchronize()
+    # reference: conv1d over tokens (taps) == GEMM
+    x = A.float().transpose(1, 2)                         # [batch, K, M]
+    w = W.float().permute(0, 2, 1).contiguous()           # [N, K, taps]
+    y = F.conv1d(x, w, b, padding=(taps - 1) // 2).transpose(1, 2)   # [batch, M, N]
+    if act == lib.ACT_GELU_NEW:
+        y = F.gelu(y, approximate="tanh")
+    elif act == lib.ACT_SILU:
+        y = F.silu(y)
+    elif act == lib.ACT_LRELU02:
+        y = F.leaky_relu(y, 0.2)
+    elif act == lib.ACT_GEGLU:
+        y = y[..., 0::2] * F.gelu(y[..., 1::2])
+    if residual:
+        y = y + res
+    return y, of, ob
+
+
+CASES = [
+    dict(M=128, N=128, K=64),
+    dict(M=128, N=128, K=64, tile_n=64),
+    dict(M=128, N=256, K=256, tile_n=128),
+    dict(M=300, N=200, K=128),                       # M and N tails
+    dict(M=1, N=8194, K=128),                        # lm-head at M=1
+    dict(M=256, N=3072, K=1024, out="bf16"),         # AR c_attn at B=256
+    dict(M=256, N=1024, K=4096, residual=True),      # AR mlp.c_proj (+residual)
+    dict(M=256, N=4096, K=1024, act=1, out="bf16"),  # c_fc + gelu_new
+    dict(M=333, N=256, K=128, taps=3, batch=2, residual=True),  # conv k=3, batch boundaries
+    dict(M=374, N=1024, K=1024, taps=3, batch=2, tile_n=128),
+    dict(M=150, N=512, K=128, act=3, out="bf16"),    # GEGLU
+    dict(M=77, N=200, K=1024, taps=3),               # diffusion out conv (N=200)
+    dict(M=1882, N=24832, K=64, taps=3),             # UnivNet kernel predictor
+    dict(M=130, N=192, K=64, act=2, out="both"),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(i) for i in range(len(CASES))])
+def test_gemm_tcgen05(case):
+    y, of, ob = _run(**case)
+    scale = y.abs().max().item()
+    if of is not None:
+        err = (of - y).abs().max().item()
+        report("gemm_tc_f32 %s" % case, err / scale)
+        assert err / scale < 2e-3, (err, scale)
+    if ob is not None:
+        err = (ob.float() - y).abs().max().item()
+        report("gemm_tc_bf16 %s" % case, err / scale)
+        assert err / scale < 1e-2, (err, scale)
+
+
+@pytest.mark.parametrize("case", [CASES[3], CASES[8], CASES[10]], ids=["tails", "conv3", "geglu"])
+def test_gemm_simt_checker(case):
+    y, of, ob = _run(force_ref=True, **case)
+    scale = y.abs().max().item()
+    got = of if of is not None else ob.float()
+    err = (got - y).abs().max().item()
+    report("gemm_ref %s" % case, err / scale)
+    assert err / scale < 1e-2

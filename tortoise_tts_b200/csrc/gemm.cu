@@ -115,7 +115,7 @@ struct GemmSmem {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
-                    int K, int taps, int pad, GemmEpilogue ep) {
+                    int K, int taps, int pad, int a_batch_mul, GemmEpilogue ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using L = GemmSmem<BN, STAGES>;
@@ -156,7 +156,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         uint8_t* sa = smem + stage * L::STAGE_BYTES;
         uint8_t* sb = sa + L::A_BYTES;
         mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-        tma_load_3d(sa, &map_a, &full_bar[stage], kk, m0 + tap - pad, bz);
+        tma_load_3d(sa, &map_a, &full_bar[stage], kk, m0 + tap - pad, bz * a_batch_mul);
         tma_load_3d(sb, &map_b, &full_bar[stage], tap * K + kk, n0, 0);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -323,8 +323,11 @@ static int g_gemm_impl = -1;  // 0 = tcgen05, 1 = SIMT reference (bring-up only;
 template <int BN, int STAGES>
 static int launch_tc(const TtbGemmArgs& g, const GemmEpilogue& ep, cudaStream_t st) {
   CUtensorMap ma, mb;
-  if (get_tensor_map_bf16(&ma, g.A, (uint64_t)g.K, (uint64_t)g.rows, (uint64_t)g.batch, (uint64_t)g.lda,
-                          (uint64_t)g.a_bstride, BK, BM)) return -1;
+  // a_bstride == 0 broadcasts one activation tensor to every batch item (batch dim of extent 1, coordinate 0)
+  const bool bcast = (g.batch == 1) || (g.a_bstride == 0);
+  const uint64_t a_d2 = bcast ? 1 : (uint64_t)g.batch;
+  const uint64_t a_s2 = bcast ? (uint64_t)g.rows * g.lda : (uint64_t)g.a_bstride;
+  if (get_tensor_map_bf16(&ma, g.A, (uint64_t)g.K, (uint64_t)g.rows, a_d2, (uint64_t)g.lda, a_s2, BK, BM)) return -1;
   if (get_tensor_map_bf16(&mb, g.W, (uint64_t)g.K * g.taps, (uint64_t)g.N, 1, (uint64_t)g.K * g.taps,
                           (uint64_t)g.K * g.taps * g.N, BK, BN)) return -1;
   using L = GemmSmem<BN, STAGES>;
@@ -335,7 +338,7 @@ static int launch_tc(const TtbGemmArgs& g, const GemmEpilogue& ep, cudaStream_t 
     attr_set = true;
   }
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.batch);
-  gemm_bf16_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, st>>>(ma, mb, g.M, g.N, g.K, g.taps, g.pad, ep);
+  gemm_bf16_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, st>>>(ma, mb, g.M, g.N, g.K, g.taps, g.pad, bcast ? 0 : 1, ep);
   TTB_CHECK_LAUNCH("gemm_bf16_tc_kernel");
   return 0;
 }
