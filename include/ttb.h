@@ -172,8 +172,9 @@ int ttb_voc_convt(const float* x, int C, int L, const float* w, const float* b, 
  * bias fp32 [F, ldb] at column boff laid out [oc]. */
 int ttb_voc_lvc_gate(const float* y, int C, int L, int hop, const float* kernels, int ldk, int koff, const float* bias,
                      int ldb, int boff, float* x, void* stream);
-/* channel-major fp32 [C, L] -> token-major bf16 [L, ldo] (feeds the kernel-predictor GEMM) */
-int ttb_voc_to_tokens_bf16(const float* x, int C, int L, void* out, int ldo, void* stream);
+/* channel-major fp32 [C, L] -> token-major bf16 [L, ldo] (feeds the kernel-predictor GEMM). split != 0 writes the
+ * error-compensated triple [hi | lo | hi] (ldo >= 3C) to be contracted with weights packed as [Wh | Wh | Wl]. */
+int ttb_voc_to_tokens_bf16(const float* x, int C, int L, void* out, int ldo, int split, void* stream);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,9 @@ def pytest_configure(config):
 
 def pytest_collection_modifyitems(config, items):
     import torch
+    # PyTorch references used by the tests must be true fp32 (no TF32 in cuBLAS / cuDNN)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
     from oracle.ref_shims import reference_available
     has_gpu = torch.cuda.is_available()
     has_ref = reference_available()

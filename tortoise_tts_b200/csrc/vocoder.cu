@@ -154,7 +154,10 @@ voc_lvc_gate_kernel(const float* __restrict__ y, int C, int L, int hop, const fl
   }
 }
 
-__global__ void voc_to_tokens_kernel(const float* __restrict__ x, int C, int L, __nv_bfloat16* __restrict__ out, int ldo) {
+// channel-major fp32 -> token-major bf16. split != 0 writes the error-compensated triple [hi | lo | hi] per row
+// (x = hi + lo to ~16 mantissa bits) so that one bf16 GEMM against [Wh | Wh | Wl] reproduces fp32-grade accuracy.
+__global__ void voc_to_tokens_kernel(const float* __restrict__ x, int C, int L, __nv_bfloat16* __restrict__ out, int ldo,
+                                     int split) {
   __shared__ float tile[32][33];
   const int l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += 8) {
@@ -164,7 +167,17 @@ __global__ void voc_to_tokens_kernel(const float* __restrict__ x, int C, int L, 
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int l = l0 + i, c = c0 + threadIdx.x;
-    if (l < L && c < ldo) out[(long long)l * ldo + c] = __float2bfloat16(c < C ? tile[threadIdx.x][i] : 0.f);
+    if (l >= L) continue;
+    const float v = (c < C) ? tile[threadIdx.x][i] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16(v);
+    if (!split) {
+      if (c < ldo) out[(long long)l * ldo + c] = hi;
+    } else if (c < C) {
+      const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+      out[(long long)l * ldo + c] = hi;
+      out[(long long)l * ldo + C + c] = lo;
+      out[(long long)l * ldo + 2 * C + c] = hi;
+    }
   }
 }
 
@@ -215,9 +228,10 @@ extern "C" int ttb_voc_lvc_gate(const float* y, int C, int L, int hop, const flo
   return 0;
 }
 
-extern "C" int ttb_voc_to_tokens_bf16(const float* x, int C, int L, void* out, int ldo, void* stream) {
-  dim3 grid((L + 31) / 32, (ldo + 31) / 32), block(32, 8);
-  voc_to_tokens_kernel<<<grid, block, 0, ST>>>(x, C, L, reinterpret_cast<__nv_bfloat16*>(out), ldo);
+extern "C" int ttb_voc_to_tokens_bf16(const float* x, int C, int L, void* out, int ldo, int split, void* stream) {
+  if (split && ldo < 3 * C) { set_error("ttb_voc_to_tokens_bf16: split needs ldo >= 3*C"); return -1; }
+  dim3 grid((L + 31) / 32, ((split ? C : ldo) + 31) / 32), block(32, 8);
+  voc_to_tokens_kernel<<<grid, block, 0, ST>>>(x, C, L, reinterpret_cast<__nv_bfloat16*>(out), ldo, split);
   TTB_CHECK_LAUNCH("voc_to_tokens_kernel");
   return 0;
 }

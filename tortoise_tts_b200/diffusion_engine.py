@@ -272,6 +272,37 @@ class DiffusionEngine:
         self._ws = st
         return st
 
+    def _prepare_time(self, st, t_list):
+        """time_embed(timestep_embedding(t)) and every ResBlock's emb_layers for the given ORIGINAL-scale timesteps
+        (one row per call) -> st['ss_all'] [n_res, n, 2C] (diffusion_decoder.py:294, 109-114)."""
+        C, dev, n = self.C, self.dev, len(t_list)
+        t_call = torch.tensor(t_list, dtype=torch.int32, device=dev)
+        te = torch.empty(n, C, dtype=torch.float32, device=dev)
+        lib.timestep_embedding(t_call, n, C, te)
+        t1 = torch.empty(n, C, dtype=torch.float32, device=dev)
+        lib.linear_small(te, n, C, self.te_w0, self.te_b0, C, t1, silu_out=True)
+        temb = torch.empty(n, C, dtype=torch.float32, device=dev)
+        lib.linear_small(t1, n, C, self.te_w2, self.te_b2, C, temb)
+        for j, rw in enumerate(self.res_all):
+            lib.linear_small(temb, n, C, rw.w_emb, rw.b_emb, 2 * C, st["ss_all"][j], silu_in=True)
+
+    def forward_once(self, x, t_orig, code_emb):
+        """Parity hook ≙ DiffusionTts.forward(x, t, precomputed_aligned_embeddings) and (..., conditioning_free=True)
+        (diffusion_decoder.py:262-322): x fp32 [100, S] channel-major, t_orig original-scale timestep, code_emb [S, C].
+        Returns (cond_out, uncond_out) fp32 [200, S]."""
+        C, dev = self.C, self.dev
+        S = x.shape[-1]
+        st = self._state(S, 2, 1, -1.0)
+        st["code_emb_init"][0].copy_(code_emb)
+        lib.broadcast_rows(self.uncond, S, C, st["code_emb_init"][1], None, C)
+        self._prepare_time(st, [int(t_orig)])
+        lib.transpose_f32(_f(x.reshape(self.cin, S), dev), self.cin, S, st["x"])
+        lib.cast_pad_bf16(st["x"], S, self.cin, self.cin, st["x_bf"], self.cin_pad)
+        st["counter"].zero_()
+        self._forward(st)
+        mo = st["model_out"]
+        return mo[0].t().contiguous(), mo[1].t().contiguous()
+
     def sample(self, latents, cond_latent, iters, noise0, step_noise, cond_free=True, cond_free_k=2.0, use_graph=True,
                return_trace=False):
         """≙ do_spectrogram_diffusion (api.py:117-130). latents [N, ar_dim], cond_latent [2C];
@@ -291,15 +322,7 @@ class DiffusionEngine:
             lib.broadcast_rows(self.uncond, S, C, st["code_emb_init"][1], None, C)
         st["tables"].copy_(torch.from_numpy(tables))
         # time embeddings of all steps in call order (i = n-1 ... 0), then every ResBlock's emb_layers
-        t_call = torch.tensor([int(tmap[n - 1 - c]) for c in range(n)], dtype=torch.int32, device=dev)
-        te = torch.empty(n, C, dtype=torch.float32, device=dev)
-        lib.timestep_embedding(t_call, n, C, te)
-        t1 = torch.empty(n, C, dtype=torch.float32, device=dev)
-        lib.linear_small(te, n, C, self.te_w0, self.te_b0, C, t1, silu_out=True)
-        temb = torch.empty(n, C, dtype=torch.float32, device=dev)
-        lib.linear_small(t1, n, C, self.te_w2, self.te_b2, C, temb)
-        for j, rw in enumerate(self.res_all):
-            lib.linear_small(temb, n, C, rw.w_emb, rw.b_emb, 2 * C, st["ss_all"][j], silu_in=True)
+        self._prepare_time(st, [int(tmap[n - 1 - c]) for c in range(n)])
         # state: x_T and the pre-drawn noises, token-major
         lib.transpose_f32(_f(noise0.reshape(self.cin, S), dev), self.cin, S, st["x"])
         lib.cast_pad_bf16(st["x"], S, self.cin, self.cin, st["x_bf"], self.cin_pad)
@@ -321,9 +344,11 @@ class DiffusionEngine:
                 g = torch.cuda.CUDAGraph()
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
+                c0 = lib.CALLS
                 with torch.cuda.stream(side):
                     with torch.cuda.graph(g, stream=side):
                         one()
+                st["graph_calls"] = lib.CALLS - c0
                 torch.cuda.current_stream().wait_stream(side)
                 st["graph"] = g
                 st["counter"].zero_()
@@ -331,6 +356,7 @@ class DiffusionEngine:
                 lib.cast_pad_bf16(st["x"], S, self.cin, self.cin, st["x_bf"], self.cin_pad)
             for _ in range(n):
                 st["graph"].replay()
+            lib.add_calls(n * st["graph_calls"])
         else:
             for _ in range(n):
                 one()

@@ -72,7 +72,17 @@ def load():
     return lib
 
 
+CALLS = 0   # number of C-ABI compute calls issued (each launches >= 1 kernel); graph replays add their captured count
+
+
+def add_calls(n):
+    global CALLS
+    CALLS += n
+
+
 def _chk(rc, what):
+    global CALLS
+    CALLS += 1
     if rc != 0:
         raise TtbError("%s failed (%d): %s" % (what, rc, load().ttb_last_error().decode()))
 
@@ -243,5 +253,6 @@ def voc_lvc_gate(y, Cc, L, hop, kernels, ldk, koff, bias, ldb, boff, x):
                                  _p(_f32(x)), _stream()), "ttb_voc_lvc_gate")
 
 
-def voc_to_tokens_bf16(x, Cc, L, out, ldo):
-    _chk(load().ttb_voc_to_tokens_bf16(_p(_f32(x)), Cc, L, _p(_bf(out)), ldo, _stream()), "ttb_voc_to_tokens_bf16")
+def voc_to_tokens_bf16(x, Cc, L, out, ldo, split=False):
+    _chk(load().ttb_voc_to_tokens_bf16(_p(_f32(x)), Cc, L, _p(_bf(out)), ldo, 1 if split else 0, _stream()),
+         "ttb_voc_to_tokens_bf16")

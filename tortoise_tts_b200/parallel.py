@@ -1,0 +1,57 @@
+"""Candidate / utterance sharding across the GPUs of one box.
+
+One process per GPU (torch.distributed, NCCL over NVLink; gloo in the CPU tests). The hot path shards without any
+per-step collective: autoregressive candidates are independent given (text tokens, conditioning latent), so rank r
+decodes candidates [r*B/G, (r+1)*B/G) and scores them with CLVP locally; ONE all-gather of {scores f32, codes i32}
+lets every rank run the same top-k; the k selected candidates' latents / diffusion / vocoder run on rank j % G and
+the waveforms are broadcast from their owners. The reference has no distributed code: this is new.
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(total, rank, world_size):
+    """Contiguous, balanced split of `total` candidates: returns (lo, hi) for `rank`."""
+    per = (total + world_size - 1) // world_size
+    lo = min(total, rank * per)
+    return lo, min(total, lo + per)
+
+
+def owner_of(j, world_size):
+    """Rank that renders the j-th selected candidate (diffusion + vocoder)."""
+    return j % world_size
+
+
+def gather_candidates(scores, codes, total):
+    """All-gather of per-rank CLVP scores [b] and codes [b, L] -> ([total], [total, L]) in global candidate order.
+    One fused collective: scores are bit-cast into an extra int32 column of the codes buffer."""
+    rank, ws = world()
+    if ws == 1:
+        return scores, codes
+    per = (total + ws - 1) // ws
+    L = codes.shape[1]
+    buf = torch.zeros(per, L + 1, dtype=torch.int32, device=codes.device)
+    n = codes.shape[0]
+    buf[:n, :L] = codes
+    buf[:n, L] = scores.contiguous().view(torch.int32)
+    out = torch.empty(ws * per, L + 1, dtype=torch.int32, device=codes.device)
+    dist.all_gather_into_tensor(out, buf) if codes.is_cuda else dist.all_gather(list(out.chunk(ws)), buf)
+    keep = torch.cat([out[r * per: r * per + (shard_range(total, r, ws)[1] - shard_range(total, r, ws)[0])]
+                      for r in range(ws)], dim=0)
+    return keep[:, L].contiguous().view(torch.float32), keep[:, :L].contiguous()
+
+
+def broadcast_from_owner(t, numel, owner, device, dtype=torch.float32):
+    """Every rank ends up with the owner's 1-D tensor of `numel` elements."""
+    rank, ws = world()
+    if ws == 1:
+        return t
+    buf = t.contiguous() if rank == owner else torch.empty(numel, dtype=dtype, device=device)
+    dist.broadcast(buf, src=owner)
+    return buf

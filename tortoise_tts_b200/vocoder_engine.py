@@ -48,7 +48,12 @@ class VocoderEngine:
             bw = _fold(sd, kp + "bias_conv.")                        # [nl*2ch, hid, 3]
             bb = sd[kp + "bias_conv.bias"].float()
             w_all = torch.cat([kw[idx], bw], dim=0)                  # [N, hid, 3]
-            blk["kp_w"] = w_all.permute(0, 2, 1).reshape(w_all.shape[0], 3 * hid).to(device=dev, dtype=torch.bfloat16).contiguous()
+            # error-compensated bf16 split (x = hi + lo): per tap the K axis is [Wh | Wh | Wl] against activations
+            # [xh | xl | xh], i.e. xh*Wh + xl*Wh + xh*Wl ~ fp32-grade products on the bf16 tensor pipe
+            wt = w_all.permute(0, 2, 1).contiguous()                 # [N, 3 taps, hid]
+            wh = wt.to(torch.bfloat16)
+            wl = (wt - wh.float()).to(torch.bfloat16)
+            blk["kp_w"] = torch.cat([wh, wh, wl], dim=2).reshape(wt.shape[0], 3 * 3 * hid).to(dev).contiguous()
             blk["kp_b"] = _f(torch.cat([kb[idx], bb], dim=0), dev)
             blk["conv"] = [(_f(_fold(sd, p + f"conv_blocks.{d}.1."), dev), _f(sd[p + f"conv_blocks.{d}.1.bias"], dev))
                            for d in range(self.nl)]
@@ -70,7 +75,7 @@ class VocoderEngine:
         c1 = torch.empty(hid, F, dtype=torch.float32, device=dev)
         c2 = torch.empty(hid, F, dtype=torch.float32, device=dev)
         c3 = torch.empty(hid, F, dtype=torch.float32, device=dev)
-        tok = torch.empty(F, hid, dtype=torch.bfloat16, device=dev)
+        tok = torch.empty(F, 3 * hid, dtype=torch.bfloat16, device=dev)
         kern = torch.empty(F, self.kp_n, dtype=torch.float32, device=dev)
         for blk in self.blocks:
             s = blk["stride"]
@@ -85,8 +90,8 @@ class VocoderEngine:
                 lib.voc_conv1d(cur, hid, F, w1, b1, hid, 3, c2, lrelu_out=VOC_LRELU)
                 lib.voc_conv1d(c2, hid, F, w2, b2, hid, 3, nxt, lrelu_out=VOC_LRELU, residual=cur)
                 cur, nxt = nxt, cur
-            lib.voc_to_tokens_bf16(cur, hid, F, tok, hid)
-            lib.gemm(tok, blk["kp_w"], M=F, N=self.kp_n, K=hid, taps=3, pad=1, bias=blk["kp_b"], out_f32=kern)
+            lib.voc_to_tokens_bf16(cur, hid, F, tok, 3 * hid, split=True)
+            lib.gemm(tok, blk["kp_w"], M=F, N=self.kp_n, K=3 * hid, taps=3, pad=1, bias=blk["kp_b"], out_f32=kern)
             y = torch.empty(ch, L, dtype=torch.float32, device=dev)
             for i, d in enumerate(VOC_DILATIONS):
                 w, b = blk["conv"][i]
