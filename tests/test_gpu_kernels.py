@@ -63,7 +63,9 @@ def test_groupnorm_fused(C, groups, S):
 
 
 @pytest.mark.parametrize("T,H,nseq,causal,use_bias", [(45, 2, 2, False, True), (174, 16, 1, True, False),
-                                                      (374, 16, 2, False, True), (130, 12, 3, False, False)])
+                                                      (374, 16, 2, False, True), (130, 12, 3, False, False),
+                                                      (64, 2, 1, False, False), (128, 2, 2, True, True),
+                                                      (1872, 16, 2, False, True), (676, 16, 1, True, False)])
 def test_attention(T, H, nseq, causal, use_bias):
     from tortoise_tts_b200 import lib
     torch.manual_seed(3)

@@ -166,22 +166,45 @@ ar_decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16
     lsum += p;
   }
   const float denom = block_sum(lsum, red);  // contains __syncthreads -> dsm visible
-  // PV: warp w takes positions j = w, w+4, ...; lane owns dims 2*lane, 2*lane+1
+  // PV: 16-byte loads; a warp covers 4 positions x 8 dim-chunks per instruction, 4 instructions in flight.
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float a0 = 0.f, a1 = 0.f;
-  for (int j = w; j < ctx; j += DEC_THREADS / 32) {
-    const __nv_bfloat16* vr = (j < P) ? pvb + (long long)j * 64 : cvb + (long long)(j - P) * 64;
-    const uint32_t u = reinterpret_cast<const uint32_t*>(vr)[lane];
-    const float2 f = unpack_bf16(u);
-    const float p = dsm[j];
-    a0 += p * f.x; a1 += p * f.y;
+  const int psub = lane >> 3, dch = lane & 7;       // position within the group of 4, 8-dim chunk
+  float acc[8];
+#pragma unroll
+  for (int d = 0; d < 8; ++d) acc[d] = 0.f;
+  constexpr int NW = DEC_THREADS / 32;
+  for (int j0 = w * 16; j0 < ctx; j0 += NW * 16) {
+    uint4 u[4];
+    float pr[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = j0 + i * 4 + psub;
+      const bool ok = j < ctx;
+      const __nv_bfloat16* vr = (j < P) ? pvb + (long long)j * 64 : cvb + (long long)(j - P) * 64;
+      u[i] = ok ? reinterpret_cast<const uint4*>(vr)[dch] : make_uint4(0, 0, 0, 0);
+      pr[i] = ok ? dsm[j] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f0 = unpack_bf16(u[i].x), f1 = unpack_bf16(u[i].y), f2 = unpack_bf16(u[i].z), f3 = unpack_bf16(u[i].w);
+      acc[0] += pr[i] * f0.x; acc[1] += pr[i] * f0.y; acc[2] += pr[i] * f1.x; acc[3] += pr[i] * f1.y;
+      acc[4] += pr[i] * f2.x; acc[5] += pr[i] * f2.y; acc[6] += pr[i] * f3.x; acc[7] += pr[i] * f3.y;
+    }
   }
-  part[w][2 * lane] = a0; part[w][2 * lane + 1] = a1;
+#pragma unroll
+  for (int d = 0; d < 8; ++d) {
+    acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], 8);
+    acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], 16);
+  }
+  if (psub == 0) {
+#pragma unroll
+    for (int d = 0; d < 8; ++d) part[w][dch * 8 + d] = acc[d];
+  }
   __syncthreads();
   if (threadIdx.x < 64) {
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < DEC_THREADS / 32; ++i) s += part[i][threadIdx.x];
+    for (int i = 0; i < NW; ++i) s += part[i][threadIdx.x];
     out[(long long)b * D + h * 64 + threadIdx.x] = __float2bfloat16(s / denom);
   }
 }
