@@ -98,9 +98,10 @@ def kernel_probes(tts, cfg, n_mel, B, P):
     # (1) diffusion attention: B=2 (cond+uncond), 16 heads, S x S, relative-position bias
     qkv = torch.randn(2 * S, 3 * C, device=dev).to(torch.bfloat16)
     o = torch.empty(2 * S, C, device=dev, dtype=torch.bfloat16)
-    bias = torch.randn(H, 2 * S - 1, device=dev)
-    ms = timeit(lambda: lib.attention(qkv, o, nseq=2, T=S, H=H, ld=3 * C, ldo=C, k_off=C, v_off=2 * C, scale=0.125, bias=bias),
-                flush=flush)
+    from tortoise_tts_b200.diffusion_engine import _rel_pos_table
+    bias = _rel_pos_table(torch.randn(32, H, device=dev), S, 8.0)      # T5 table as the denoiser uses it
+    ms = timeit(lambda: lib.attention(qkv, o, nseq=2, T=S, H=H, ld=3 * C, ldo=C, k_off=C, v_off=2 * C, scale=0.125, bias=bias,
+                                      bias_sat=64), flush=flush)
     flops = 2 * H * 4.0 * S * S * 64
     out.append(dict(kernel="diffusion attention (2x16 heads, S=%d)" % S, bound="tensor", ms=ms, count=13 * 200,
                     achieved=flops / ms / 1e9, peak=tfl, unit="TFLOP/s"))

@@ -41,8 +41,10 @@ typedef struct TtbGemmArgs {
   int batch;
   int act;              /* TTB_ACT_* ; GEGLU expects W rows interleaved (u0,g0,u1,g1,..) and writes N/2 columns */
   float alpha;          /* accumulator scale */
-  int tile_n;           /* 0 = auto, 64 or 128 */
+  int tile_n;           /* 0 = auto, 32, 64 or 128 */
   int force_ref;        /* 1 = SIMT checker kernel (tests only) */
+  int splitk;           /* > 1: split the reduction over grid.z; writes raw fp32 partials out_f32[split][M][ldo]
+                           (outf_bstride = stride between splits); batch must be 1, no epilogue fusion */
 } TtbGemmArgs;
 
 /* nn.Linear / HF Conv1D / nn.Conv1d(k=1,3) as one tcgen05 GEMM with fused bias/activation/residual.
@@ -57,6 +59,12 @@ int ttb_gemm(const TtbGemmArgs* args, void* stream);
  * autoregressive.py:42,174,348). x fp32 [M, D]; writes bf16 and/or fp32. */
 int ttb_layernorm(const float* x, int M, int D, const float* g1, const float* b1, const float* g2, const float* b2,
                   void* out_bf16, float* out_f32, void* stream);
+/* Residual update fused with the LayerNorm that follows it (and with the split-K reduction of the GEMM before it):
+ *   x[m,:] += bias + sum_s partials[s][m,:]   (written back, fp32);   y = LN(x) (optionally chained with a 2nd LN).
+ * GPT-2 block glue `h = x + c_proj(...)` -> `ln_2(h)` (HF modeling_gpt2 GPT2Block via autoregressive.py:150-163). */
+int ttb_residual_layernorm(float* x, int M, int D, const float* partials, int nsplit, long long split_stride,
+                           const float* bias, const float* g1, const float* b1, const float* g2, const float* b2,
+                           void* out_bf16, float* out_f32, void* stream);
 /* x / max(||x|| * D^-0.5, 1e-8) * g   (xtransformers.py:335-344) */
 int ttb_rmsnorm(const float* x, int M, int D, const float* g, void* out_bf16, void* stream);
 /* GroupNorm32 over token-major x [B, S, C] (arch_util.py:21-41) fused with the consumers that follow it in
@@ -77,6 +85,8 @@ typedef struct TtbAttnArgs {
   int ld, ldo, k_off, v_off;
   float scale;          /* applied to q.k */
   int causal;
+  int bias_sat;         /* > 0: bias[h][r] == bias[h][-(T-1)] for r <= -bias_sat and == bias[h][T-1] for r >= bias_sat
+                           (T5 buckets saturate at max_distance); lets far-from-diagonal tiles skip the table. 0 = unknown */
 } TtbAttnArgs;
 /* softmax(q k^T * scale + bias) v per (sequence, head), head_dim 64. Replaces QKVAttentionLegacy
  * (arch_util.py:44-77), HF GPT2Attention._attn, and xtransformers Attention (xtransformers.py:660-712). */

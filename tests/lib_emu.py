@@ -16,7 +16,7 @@ def _v(t, sizes, strides):
 
 def gemm(A, W, *, M, N, K, bias=None, residual=None, out_f32=None, out_bf16=None, lda=None, rows=None, batch=1,
          a_bstride=0, res_bstride=0, outf_bstride=0, outb_bstride=0, ldr=None, ldo=None, ldob=None, taps=1, pad=0,
-         act=ACT_NONE, alpha=1.0, tile_n=0, force_ref=False):
+         act=ACT_NONE, alpha=1.0, tile_n=0, force_ref=False, splitk=1):
     n_out = N // 2 if act == ACT_GEGLU else N
     lda = K if lda is None else lda
     rows = M if rows is None else rows
@@ -44,6 +44,14 @@ def gemm(A, W, *, M, N, K, bias=None, residual=None, out_f32=None, out_bf16=None
         acc = F.leaky_relu(acc, 0.2)
     if residual is not None and act != ACT_GEGLU:
         acc = acc + _v(residual, (batch, M, n_out), (res_bstride, ldr, 1))
+    if splitk > 1:   # raw partials: the whole sum in split 0, zeros elsewhere (only the sum is observable)
+        kb_total = (K // 64) * taps
+        per = (kb_total + splitk - 1) // splitk
+        nz = (kb_total + per - 1) // per
+        o = _v(out_f32, (nz, M, n_out), (outf_bstride, ldo, 1))
+        o.zero_()
+        o[0].copy_(acc[0])
+        return
     if out_f32 is not None:
         _v(out_f32, (batch, M, n_out), (outf_bstride, ldo, 1)).copy_(acc)
     if out_bf16 is not None:
@@ -58,6 +66,14 @@ def layernorm(x, M, D, g1, b1, g2=None, b2=None, out_bf16=None, out_f32=None):
         _v(out_bf16, (M, D), (D, 1)).copy_(y.to(torch.bfloat16))
     if out_f32 is not None:
         _v(out_f32, (M, D), (D, 1)).copy_(y)
+
+
+def residual_layernorm(x, M, D, partials, nsplit, split_stride, bias, g1, b1, g2=None, b2=None, out_bf16=None,
+                       out_f32=None):
+    xx = _v(x, (M, D), (D, 1))
+    t = _v(partials, (nsplit, M, D), (split_stride, D, 1)).sum(dim=0)
+    xx += t + (bias if bias is not None else 0.0)
+    layernorm(x, M, D, g1, b1, g2, b2, out_bf16, out_f32)
 
 
 def rmsnorm(x, M, D, g, out_bf16):
@@ -84,7 +100,7 @@ def groupnorm(x, B, S, Cc, groups, gamma, beta, partials, scale_shift=None, ss_b
         _v(out_f32, (B, S, Cc), (S * ldof, ldof, 1)).copy_(y)
 
 
-def attention(qkv, out, *, nseq, T, H, ld, ldo, k_off, v_off, scale, causal=False, bias=None):
+def attention(qkv, out, *, nseq, T, H, ld, ldo, k_off, v_off, scale, causal=False, bias=None, bias_sat=0):
     base = _v(qkv, (nseq, T, ld), (T * ld, ld, 1)).float()
     q = base[..., :H * 64].reshape(nseq, T, H, 64).transpose(1, 2)
     k = base[..., k_off:k_off + H * 64].reshape(nseq, T, H, 64).transpose(1, 2)

@@ -84,6 +84,40 @@ def test_gemm_tcgen05(case):
         assert err / scale < 1e-2, (err, scale)
 
 
+@pytest.mark.parametrize("M,N,K,tile_n,splitk", [(256, 1024, 1024, 32, 2), (256, 1024, 4096, 32, 4), (256, 3072, 1024, 32, 1),
+                                                 (100, 128, 128, 32, 2), (256, 1024, 4096, 64, 3)])
+def test_gemm_skinny_splitk(M, N, K, tile_n, splitk):
+    """Decode-shape GEMMs: 32-column tiles and split-K partials whose fixed-order sum equals the full product."""
+    from tortoise_tts_b200 import lib
+    A = _mk((M, K), 1.0, 5).to(torch.bfloat16)
+    W = _mk((N, K), K ** -0.5, 6).to(torch.bfloat16)
+    want = (A.float().cpu() @ W.float().cpu().t()).cuda()
+    if splitk == 1:
+        b = _mk((N,), 0.5, 7)
+        out = torch.empty(M, N, device="cuda")
+        lib.gemm(A, W, M=M, N=N, K=K, bias=b, out_f32=out, tile_n=tile_n)
+        got = out - b
+    else:
+        kb = K // 64
+        per = (kb + splitk - 1) // splitk
+        nz = (kb + per - 1) // per
+        part = torch.full((nz, M, N), float("nan"), device="cuda")
+        lib.gemm(A, W, M=M, N=N, K=K, out_f32=part, outf_bstride=M * N, tile_n=tile_n, splitk=splitk)
+        got = part.sum(dim=0)
+        # and through the fused residual + LayerNorm consumer
+        x = _mk((M, N), 1.0, 8)
+        x0 = x.clone()
+        bias, g, bb = _mk((N,), 0.5, 9), _mk((N,), 1.0, 10), _mk((N,), 1.0, 11)
+        y = torch.empty(M, N, device="cuda")
+        lib.residual_layernorm(x, M, N, part, nz, M * N, bias, g, bb, out_f32=y)
+        xr = x0 + bias + want
+        assert (x - xr).abs().max().item() < 2e-3 * xr.abs().max().item()
+        assert (y - F.layer_norm(xr, (N,), g, bb, 1e-5)).abs().max().item() < 5e-3
+    err = (got - want).abs().max().item() / want.abs().max().item()
+    report("gemm skinny M=%d N=%d K=%d tile=%d splitk=%d" % (M, N, K, tile_n, splitk), err)
+    assert err < 2e-3
+
+
 @pytest.mark.parametrize("case", [CASES[3], CASES[8], CASES[10]], ids=["tails", "conv3", "geglu"])
 def test_gemm_simt_checker(case):
     y, of, ob = _run(force_ref=True, **case)

@@ -65,16 +65,26 @@ def test_groupnorm_fused(C, groups, S):
 @pytest.mark.parametrize("T,H,nseq,causal,use_bias", [(45, 2, 2, False, True), (174, 16, 1, True, False),
                                                       (374, 16, 2, False, True), (130, 12, 3, False, False),
                                                       (64, 2, 1, False, False), (128, 2, 2, True, True),
-                                                      (1872, 16, 2, False, True), (676, 16, 1, True, False)])
+                                                      (1872, 16, 2, False, True), (676, 16, 1, True, False),
+                                                      (1872, 16, 2, False, "t5"), (500, 4, 1, True, "t5"),
+                                                      (300, 4, 2, False, "big")])
 def test_attention(T, H, nseq, causal, use_bias):
     from tortoise_tts_b200 import lib
+    from tortoise_tts_b200.diffusion_engine import _rel_pos_table
     torch.manual_seed(3)
     D = H * 64
-    qkv = (torch.randn(nseq * T, 3 * D, device="cuda")).to(torch.bfloat16)
-    bias = torch.randn(H, 2 * T - 1, device="cuda") if use_bias else None
+    # "big": scores spanning > 2^8 so that the lazy O rescale in TMEM is exercised
+    qkv = (torch.randn(nseq * T, 3 * D, device="cuda") * (4.0 if use_bias == "big" else 1.0)).to(torch.bfloat16)
+    sat = 0
+    if use_bias == "t5":      # saturated T5 relative-position table (fast-tile path of the flash kernel)
+        bias, sat = _rel_pos_table(torch.randn(32, H, device="cuda"), T, 8.0), 64
+    elif use_bias is True:
+        bias = torch.randn(H, 2 * T - 1, device="cuda")
+    else:
+        bias, use_bias = None, False
     out = torch.empty(nseq * T, D, device="cuda", dtype=torch.bfloat16)
     lib.attention(qkv, out, nseq=nseq, T=T, H=H, ld=3 * D, ldo=D, k_off=D, v_off=2 * D, scale=0.125, causal=causal,
-                  bias=bias)
+                  bias=bias, bias_sat=sat)
     q, k, v = (t.float().view(nseq, T, H, 64).transpose(1, 2) for t in qkv.split(D, dim=1))
     w = (q @ k.transpose(-1, -2)) * 0.125
     if use_bias:
@@ -85,7 +95,7 @@ def test_attention(T, H, nseq, causal, use_bias):
         w = w.masked_fill(~torch.ones(T, T, dtype=torch.bool, device="cuda").tril(), float("-inf"))
     want = (torch.softmax(w, -1) @ v).transpose(1, 2).reshape(nseq * T, D)
     err = (out.float() - want).abs().max().item()
-    report("attention T=%d causal=%d bias=%d" % (T, causal, use_bias), err)
+    report("attention T=%d causal=%d bias=%s" % (T, causal, use_bias), err)
     assert err < 0.03
 
 

@@ -30,6 +30,17 @@ def test_rel_pos_table_matches_oracle():
             assert torch.allclose(tab[:, j - i + T - 1], full[:, i, j])
 
 
+def test_rel_pos_table_saturates_at_max_distance():
+    """|k - q| >= 64 -> constant bias per side: the property `bias_sat=64` promises to the flash kernel."""
+    torch.manual_seed(1)
+    T = 300
+    tab = de._rel_pos_table(torch.randn(32, 3), T, 8.0)
+    c = T - 1
+    assert bool((tab[:, : c - 64 + 1] == tab[:, :1]).all())
+    assert bool((tab[:, c + 64:] == tab[:, -1:]).all())
+    assert not bool((tab[:, c - 40] == tab[:, 0]).all())
+
+
 def test_groups_rule():
     from oracle import diffusion as od
     for C in (16, 64, 128, 1024, 2048):

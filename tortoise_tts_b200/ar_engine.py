@@ -54,6 +54,15 @@ class AREngine:
         self.V = cfg.number_mel_codes
         self._dec = None  # decode workspace keyed by (B, P, Nmax)
 
+    SPLITK_PROJ = 2     # attn.c_proj  (K = D):   32 n-tiles x 2 m-tiles x 2 splits = 128 CTAs at D=1024, B=256
+    SPLITK_PROJ2 = 4    # mlp.c_proj   (K = 4D):  32 x 2 x 4 = 256 CTAs
+
+    @staticmethod
+    def _nsplit(kb_total, splitk):
+        """Number of K ranges ttb_gemm actually creates for `splitk` requested splits (every split owns >= 1 block)."""
+        per = (kb_total + splitk - 1) // splitk
+        return (kb_total + per - 1) // per
+
     # ------------------------------------------------------------------ shared trunk over M tokens
     def _alloc_trunk(self, M):
         D, dev = self.D, self.dev
@@ -120,6 +129,8 @@ class AREngine:
         st["x"] = torch.empty(B, D, dtype=torch.float32, device=dev)
         st["ws"] = self._alloc_trunk(B)
         st["hn"] = torch.empty(max(B, 1), D, dtype=torch.bfloat16, device=dev)
+        st["part_a"] = torch.zeros(max(self.SPLITK_PROJ, 2), B, D, dtype=torch.float32, device=dev)
+        st["part_b"] = torch.zeros(max(self.SPLITK_PROJ2, 2), B, D, dtype=torch.float32, device=dev)
         st["logits"] = torch.empty(B, self.V, dtype=torch.float32, device=dev)
         st["state"] = torch.zeros(64, dtype=torch.int32, device=dev)
         st["codes"] = torch.empty(B, Nmax, dtype=torch.int32, device=dev)
@@ -136,12 +147,32 @@ class AREngine:
         B, P, Nmax, D, H = st["B"], st["P"], st["Nmax"], self.D, self.H
         x, ws = st["x"], st["ws"]
         lib.ar_embed_step(st["codes"], Nmax, st["state"], self.w.mel_emb, self.w.mel_pos, B, D, sp["pos_mode"], x)
+        # Skinny-M decode (M = B candidates): every GEMM is weight-streaming bound, so the grid is widened with
+        # 32-column tiles and, for the two GEMMs that feed the residual stream, split-K; their partial sums, bias and
+        # the residual add are folded into the LayerNorm that follows (fixed summation order -> deterministic).
+        kb = D // 64
+        s1 = min(self.SPLITK_PROJ, kb)
+        s2 = min(self.SPLITK_PROJ2, 4 * kb)
+        pa, pb = st["part_a"], st["part_b"]
+        prev = None   # (partials, nsplit, bias) of the previous layer's mlp.c_proj, folded into the next LayerNorm
         for l, lw in enumerate(self.w.layers):
-            def attn(qkv, o, l=l):
-                lib.ar_decode_attention(qkv, st["pk"][l], st["pv"][l], st["ck"][l], st["cv"][l], st["state"], B, H, P,
-                                        Nmax, o)
-            self._layer(lw, x, B, ws, attn)
-        lib.layernorm(x, B, D, self.w.lnf_g, self.w.lnf_b, self.w.fn_g, self.w.fn_b, out_bf16=st["hn"])
+            if prev is None:
+                lib.layernorm(x, B, D, lw["ln1_g"], lw["ln1_b"], out_bf16=ws["a"])
+            else:
+                lib.residual_layernorm(x, B, D, prev[0], prev[1], B * D, prev[2], lw["ln1_g"], lw["ln1_b"], out_bf16=ws["a"])
+            lib.gemm(ws["a"], lw["wqkv"], M=B, N=3 * D, K=D, bias=lw["bqkv"], out_bf16=ws["qkv"], tile_n=32)
+            lib.ar_decode_attention(ws["qkv"], st["pk"][l], st["pv"][l], st["ck"][l], st["cv"][l], st["state"], B, H, P,
+                                    Nmax, ws["o"])
+            lib.gemm(ws["o"], lw["wproj"], M=B, N=D, K=D, out_f32=pa, outf_bstride=B * D, tile_n=32, splitk=max(s1, 2))
+            lib.residual_layernorm(x, B, D, pa, self._nsplit(kb, max(s1, 2)), B * D, lw["bproj"], lw["ln2_g"], lw["ln2_b"],
+                                   out_bf16=ws["a"])
+            lib.gemm(ws["a"], lw["wfc"], M=B, N=4 * D, K=D, bias=lw["bfc"], act=lib.ACT_GELU_NEW, out_bf16=ws["h"],
+                     tile_n=32)
+            lib.gemm(ws["h"], lw["wproj2"], M=B, N=D, K=4 * D, out_f32=pb, outf_bstride=B * D, tile_n=32,
+                     splitk=max(s2, 2))
+            prev = (pb, self._nsplit(4 * kb, max(s2, 2)), lw["bproj2"])
+        lib.residual_layernorm(x, B, D, prev[0], prev[1], B * D, prev[2], self.w.lnf_g, self.w.lnf_b, self.w.fn_g,
+                               self.w.fn_b, out_bf16=st["hn"])
         lib.gemm(st["hn"], self.w.w_head, M=B, N=self.V, K=D, bias=self.w.b_head, out_f32=st["logits"])
         lib.ar_sample(st["logits"], self.V, self.V, B, st["uniforms"], Nmax, st["seen"], st["codes"], Nmax,
                       st["finished"], st["state"], sp["temperature"], sp["top_k"], sp["top_p"], sp["rep_penalty"],

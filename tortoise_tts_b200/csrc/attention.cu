@@ -111,101 +111,147 @@ attn_simt_kernel(TtbAttnArgs a) {
 }
 
 // ------------------------------------------------------------------ AR decode attention
-// grid (H, B), 128 threads. ctx = P + step + 1 (the new token included).
-constexpr int DEC_THREADS = 128;
+// Single-query attention of every (candidate, head) over [shared prompt prefix | the candidate's own KV] with online
+// softmax (flash-decoding form). grid (H, ceil(B/8)); 8 warps per block, ONE CANDIDATE PER WARP, all on the same head:
+//   * the prefix K/V of this head is staged tile by tile (64 positions, 16 KB) in shared memory ONCE per block and
+//     reused by the 8 candidates (the prefix is identical for all candidates: 8x less L2->SM traffic);
+//   * the candidate's own KV is streamed from HBM with 16-byte loads: a warp instruction covers 4 positions x 8
+//     dim-chunks (512 contiguous bytes), 4 K + 4 V instructions in flight per iteration;
+//   * lane = (psub = position within the group of 4, dch = 8-dim chunk); the q.k dot product is reduced over the 8
+//     dch lanes with shuffles; every psub group keeps its own running (max, sum, acc[8]) which are merged at the end.
+// The new token's K/V is appended to the cache by the owning warp first.
+constexpr int DEC_WARPS = 8;
+constexpr int DEC_THREADS = DEC_WARPS * 32;
+constexpr int DEC_PT = 64;   // prefix positions per shared-memory tile
+
+struct DecState { float m, l; float acc[8]; };
+
+TTB_DEVINL void dec_update(DecState& st, float s, bool ok, const uint4& vv) {
+  // s is already in the log2 domain
+  const float sm = ok ? s : -INFINITY;
+  const float m_new = fmaxf(st.m, sm);
+  const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+  const float corr = exp2f(st.m - m_use);
+  const float p = exp2f(sm - m_use);
+  st.l = st.l * corr + p;
+  st.m = m_new;
+  const float2 f0 = unpack_bf16(vv.x), f1 = unpack_bf16(vv.y), f2 = unpack_bf16(vv.z), f3 = unpack_bf16(vv.w);
+  st.acc[0] = st.acc[0] * corr + p * f0.x; st.acc[1] = st.acc[1] * corr + p * f0.y;
+  st.acc[2] = st.acc[2] * corr + p * f1.x; st.acc[3] = st.acc[3] * corr + p * f1.y;
+  st.acc[4] = st.acc[4] * corr + p * f2.x; st.acc[5] = st.acc[5] * corr + p * f2.y;
+  st.acc[6] = st.acc[6] * corr + p * f3.x; st.acc[7] = st.acc[7] * corr + p * f3.y;
+}
+
+TTB_DEVINL float dec_dot(const float* q, const uint4& kk) {
+  const float2 f0 = unpack_bf16(kk.x), f1 = unpack_bf16(kk.y), f2 = unpack_bf16(kk.z), f3 = unpack_bf16(kk.w);
+  float d = q[0] * f0.x + q[1] * f0.y + q[2] * f1.x + q[3] * f1.y + q[4] * f2.x + q[5] * f2.y + q[6] * f3.x + q[7] * f3.y;
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  d += __shfl_xor_sync(0xffffffffu, d, 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 4);
+  return d;
+}
 
 __global__ void __launch_bounds__(DEC_THREADS)
 ar_decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ pk,
                       const __nv_bfloat16* __restrict__ pv, __nv_bfloat16* __restrict__ ck,
-                      __nv_bfloat16* __restrict__ cv, const TtbArState* __restrict__ state, int H, int P, int Nmax,
+                      __nv_bfloat16* __restrict__ cv, const TtbArState* __restrict__ state, int B, int H, int P, int Nmax,
                       __nv_bfloat16* __restrict__ out) {
-  extern __shared__ float dsm[];  // scores [P + Nmax]
-  __shared__ float sq[64];
-  __shared__ float red[32];
-  __shared__ float part[DEC_THREADS / 32][64];
-  const int h = blockIdx.x, b = blockIdx.y;
+  __shared__ __align__(16) __nv_bfloat16 spk[DEC_PT * 64];
+  __shared__ __align__(16) __nv_bfloat16 spv[DEC_PT * 64];
+  const int h = blockIdx.x;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y * DEC_WARPS + w;
+  const bool active = b < B;
+  const int psub = lane >> 3, dch = lane & 7;
   const int D = H * 64;
   // decode step t (>= 1) feeds token t-1 whose K/V land in candidate slot t-1
   const int slot = state->step - 1;
-  const int nc = slot + 1;            // candidate entries incl. the new one
-  const int ctx = P + nc;
-  const __nv_bfloat16* row = qkv + (long long)b * 3 * D + h * 64;
-  __nv_bfloat16* ckb = ck + ((long long)b * H + h) * Nmax * 64;
-  __nv_bfloat16* cvb = cv + ((long long)b * H + h) * Nmax * 64;
+  const int nc = slot + 1;                     // candidate entries incl. the new one
   const __nv_bfloat16* pkb = pk + (long long)h * P * 64;
   const __nv_bfloat16* pvb = pv + (long long)h * P * 64;
-  if (threadIdx.x < 64) {
-    sq[threadIdx.x] = __bfloat162float(row[threadIdx.x]) * 0.125f;
-    ckb[(long long)slot * 64 + threadIdx.x] = row[D + threadIdx.x];
-    cvb[(long long)slot * 64 + threadIdx.x] = row[2 * D + threadIdx.x];
-  }
-  __syncthreads();
-  float q[64];
-#pragma unroll
-  for (int d = 0; d < 64; ++d) q[d] = sq[d];
-  float lmax = -INFINITY;
-  for (int j = threadIdx.x; j < ctx; j += DEC_THREADS) {
-    const __nv_bfloat16* kr = (j < P) ? pkb + (long long)j * 64 : ckb + (long long)(j - P) * 64;
-    const uint4* k4 = reinterpret_cast<const uint4*>(kr);
-    float acc = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      uint4 u = k4[i];
-      float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
-      acc += q[8 * i] * f0.x + q[8 * i + 1] * f0.y + q[8 * i + 2] * f1.x + q[8 * i + 3] * f1.y + q[8 * i + 4] * f2.x +
-             q[8 * i + 5] * f2.y + q[8 * i + 6] * f3.x + q[8 * i + 7] * f3.y;
-    }
-    dsm[j] = acc;
-    lmax = fmaxf(lmax, acc);
-  }
-  const float m = block_max(lmax, red);
-  float lsum = 0.f;
-  for (int j = threadIdx.x; j < ctx; j += DEC_THREADS) {
-    float p = __expf(dsm[j] - m);
-    dsm[j] = p;
-    lsum += p;
-  }
-  const float denom = block_sum(lsum, red);  // contains __syncthreads -> dsm visible
-  // PV: 16-byte loads; a warp covers 4 positions x 8 dim-chunks per instruction, 4 instructions in flight.
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int psub = lane >> 3, dch = lane & 7;       // position within the group of 4, 8-dim chunk
-  float acc[8];
-#pragma unroll
-  for (int d = 0; d < 8; ++d) acc[d] = 0.f;
-  constexpr int NW = DEC_THREADS / 32;
-  for (int j0 = w * 16; j0 < ctx; j0 += NW * 16) {
-    uint4 u[4];
-    float pr[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int j = j0 + i * 4 + psub;
-      const bool ok = j < ctx;
-      const __nv_bfloat16* vr = (j < P) ? pvb + (long long)j * 64 : cvb + (long long)(j - P) * 64;
-      u[i] = ok ? reinterpret_cast<const uint4*>(vr)[dch] : make_uint4(0, 0, 0, 0);
-      pr[i] = ok ? dsm[j] : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f0 = unpack_bf16(u[i].x), f1 = unpack_bf16(u[i].y), f2 = unpack_bf16(u[i].z), f3 = unpack_bf16(u[i].w);
-      acc[0] += pr[i] * f0.x; acc[1] += pr[i] * f0.y; acc[2] += pr[i] * f1.x; acc[3] += pr[i] * f1.y;
-      acc[4] += pr[i] * f2.x; acc[5] += pr[i] * f2.y; acc[6] += pr[i] * f3.x; acc[7] += pr[i] * f3.y;
+  __nv_bfloat16* ckb = ck + ((long long)(active ? b : 0) * H + h) * Nmax * 64;
+  __nv_bfloat16* cvb = cv + ((long long)(active ? b : 0) * H + h) * Nmax * 64;
+  float q[8];
+  {
+    const __nv_bfloat16* row = qkv + (long long)(active ? b : 0) * 3 * D + h * 64;
+    const uint4 uq = reinterpret_cast<const uint4*>(row)[dch];
+    const float sc = 0.125f * 1.4426950408889634f;     // 1/sqrt(64) and log2(e)
+    const float2 f0 = unpack_bf16(uq.x), f1 = unpack_bf16(uq.y), f2 = unpack_bf16(uq.z), f3 = unpack_bf16(uq.w);
+    q[0] = f0.x * sc; q[1] = f0.y * sc; q[2] = f1.x * sc; q[3] = f1.y * sc;
+    q[4] = f2.x * sc; q[5] = f2.y * sc; q[6] = f3.x * sc; q[7] = f3.y * sc;
+    if (active && lane < 16) {                   // append the new K (lanes 0-7) and V (lanes 8-15) rows
+      const uint4 nv = reinterpret_cast<const uint4*>(row + (lane < 8 ? D : 2 * D))[dch];
+      reinterpret_cast<uint4*>((lane < 8 ? ckb : cvb) + (long long)slot * 64)[dch] = nv;
     }
   }
+  DecState st;
+  st.m = -INFINITY; st.l = 0.f;
 #pragma unroll
-  for (int d = 0; d < 8; ++d) {
-    acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], 8);
-    acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], 16);
+  for (int d = 0; d < 8; ++d) st.acc[d] = 0.f;
+  // ---- phase A: shared prefix, staged in shared memory
+  for (int p0 = 0; p0 < P; p0 += DEC_PT) {
+    __syncthreads();
+    const int np = min(DEC_PT, P - p0);
+    for (int i = threadIdx.x; i < DEC_PT * 8; i += DEC_THREADS) {
+      const int r = i >> 3, c = i & 7;
+      uint4 a = make_uint4(0, 0, 0, 0), v = make_uint4(0, 0, 0, 0);
+      if (r < np) {
+        a = reinterpret_cast<const uint4*>(pkb + (long long)(p0 + r) * 64)[c];
+        v = reinterpret_cast<const uint4*>(pvb + (long long)(p0 + r) * 64)[c];
+      }
+      reinterpret_cast<uint4*>(spk)[i] = a;
+      reinterpret_cast<uint4*>(spv)[i] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r0 = 0; r0 < DEC_PT; r0 += 4) {
+      const int r = r0 + psub;
+      const uint4 kk = reinterpret_cast<const uint4*>(spk)[r * 8 + dch];
+      const uint4 vv = reinterpret_cast<const uint4*>(spv)[r * 8 + dch];
+      const float s = dec_dot(q, kk);
+      dec_update(st, s, r < np, vv);
+    }
   }
-  if (psub == 0) {
+  // ---- phase B: the candidate's own KV, streamed from global memory
+  __syncwarp();
+  if (active) {
+    for (int j0 = 0; j0 < nc; j0 += 16) {
+      uint4 kk[4], vv[4];
 #pragma unroll
-    for (int d = 0; d < 8; ++d) part[w][dch * 8 + d] = acc[d];
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * 4 + psub;
+        const bool ok = j < nc;
+        kk[u] = ok ? reinterpret_cast<const uint4*>(ckb + (long long)j * 64)[dch] : make_uint4(0, 0, 0, 0);
+        vv[u] = ok ? reinterpret_cast<const uint4*>(cvb + (long long)j * 64)[dch] : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float s = dec_dot(q, kk[u]);
+        dec_update(st, s, j0 + u * 4 + psub < nc, vv[u]);
+      }
+    }
   }
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    float s = 0.f;
+  // ---- merge the 4 position sub-streams (lanes differing in bits 3,4), then normalise
 #pragma unroll
-    for (int i = 0; i < NW; ++i) s += part[i][threadIdx.x];
-    out[(long long)b * D + h * 64 + threadIdx.x] = __float2bfloat16(s / denom);
+  for (int off = 8; off <= 16; off <<= 1) {
+    const float m_o = __shfl_xor_sync(0xffffffffu, st.m, off);
+    const float l_o = __shfl_xor_sync(0xffffffffu, st.l, off);
+    const float m_new = fmaxf(st.m, m_o);
+    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+    const float c_s = exp2f(st.m - m_use), c_o = exp2f(m_o - m_use);
+    st.l = st.l * c_s + l_o * c_o;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      const float a_o = __shfl_xor_sync(0xffffffffu, st.acc[d], off);
+      st.acc[d] = st.acc[d] * c_s + a_o * c_o;
+    }
+    st.m = m_new;
+  }
+  if (active && psub == 0) {
+    const float inv = 1.0f / st.l;
+    uint4 o = make_uint4(pack_bf16(st.acc[0] * inv, st.acc[1] * inv), pack_bf16(st.acc[2] * inv, st.acc[3] * inv),
+                         pack_bf16(st.acc[4] * inv, st.acc[5] * inv), pack_bf16(st.acc[6] * inv, st.acc[7] * inv));
+    reinterpret_cast<uint4*>(out + (long long)b * D + h * 64)[dch] = o;
   }
 }
 
@@ -239,13 +285,11 @@ extern "C" int ttb_ar_decode_attention(const void* qkv, const void* prefix_k, co
                                        void* cand_v, const TtbArState* state, int B, int H, int P, int Nmax, void* out,
                                        void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t smem = (size_t)(P + Nmax) * sizeof(float);
-  if (smem > 40 * 1024) { set_error("ttb_ar_decode_attention: context %d too long", P + Nmax); return -1; }
-  dim3 grid(H, B);
-  ar_decode_attn_kernel<<<grid, DEC_THREADS, smem, st>>>(
+  dim3 grid(H, (B + DEC_WARPS - 1) / DEC_WARPS);
+  ar_decode_attn_kernel<<<grid, DEC_THREADS, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(prefix_k),
       reinterpret_cast<const __nv_bfloat16*>(prefix_v), reinterpret_cast<__nv_bfloat16*>(cand_k),
-      reinterpret_cast<__nv_bfloat16*>(cand_v), state, H, P, Nmax, reinterpret_cast<__nv_bfloat16*>(out));
+      reinterpret_cast<__nv_bfloat16*>(cand_v), state, B, H, P, Nmax, reinterpret_cast<__nv_bfloat16*>(out));
   TTB_CHECK_LAUNCH("ar_decode_attn_kernel");
   return 0;
 }

@@ -35,7 +35,8 @@ struct FaSmem {
   static constexpr int TOTAL = BAR_OFF + 16 * 8 + 1024;
 };
 
-__global__ void __launch_bounds__(FA_THREADS, 3)
+template <int MINB>
+__global__ void __launch_bounds__(FA_THREADS, MINB)
 flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, TtbAttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -130,7 +131,17 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
     for (int j = 0; j < ntiles; ++j) {
       const int k0 = j * FA_BN;
-      if (bias_h) {
+      // Tile classification (uniform over the CTA): far from the diagonal the T5 bias is saturated, i.e. constant
+      // over the whole tile, and no key is masked -> one FFMA + one EX2 per score ("fast" tiles).
+      const bool nomask = (k0 + FA_BN <= T) && (!a.causal || k0 + FA_BN - 1 <= q0);
+      bool cbias_ok = (bias_h == nullptr);
+      float cb = 0.f;
+      if (bias_h && a.bias_sat > 0) {
+        if (k0 - q0 + (FA_BN - 1) <= -a.bias_sat) { cbias_ok = true; cb = __ldg(bias_h - (T - 1)) * 1.4426950408889634f; }
+        else if (k0 - q0 - (FA_BM - 1) >= a.bias_sat) { cbias_ok = true; cb = __ldg(bias_h + (T - 1)) * 1.4426950408889634f; }
+      }
+      const bool fast = nomask && cbias_ok;
+      if (bias_h && !fast) {
         // window of the Toeplitz bias table needed by this (q-tile, k-tile): rel = kj - qi in [k0-q0-127, k0-q0+63]
         asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's readers are done
         for (int i = st; i < 191; i += 128) {
@@ -146,14 +157,20 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       tmem_ld_32x32b_x32(tmem_s + lane_base + 32, r1);
       tmem_ld_wait();
       float mx = -INFINITY;
-      const int klim = min(T - k0, a.causal ? (qi - k0 + 1) : FA_BN);   // keys c < klim are visible to this row
+      if (fast) {
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        float v = __uint_as_float(c < 32 ? r0[c] : r1[c - 32]) * sl2;
-        if (bias_h) v += sbias[c - row + 127];
-        v = (c < klim) ? v : -INFINITY;
-        if (c < 32) r0[c] = __float_as_uint(v); else r1[c - 32] = __float_as_uint(v);
-        mx = fmaxf(mx, v);
+        for (int c = 0; c < 32; ++c) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[c]), __uint_as_float(r1[c])));
+        mx = fmaf(mx, sl2, cb);
+      } else {
+        const int klim = min(T - k0, a.causal ? (qi - k0 + 1) : FA_BN);   // keys c < klim are visible to this row
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          float v = __uint_as_float(c < 32 ? r0[c] : r1[c - 32]) * sl2;
+          if (bias_h) v += sbias[c - row + 127];
+          v = (c < klim) ? v : -INFINITY;
+          if (c < 32) r0[c] = __float_as_uint(v); else r1[c - 32] = __float_as_uint(v);
+          mx = fmaxf(mx, v);
+        }
       }
       const bool grow = mx > m + 8.0f;                 // also true for the first finite max (m = -inf)
       const float m_new = grow ? mx : m;
@@ -175,12 +192,23 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       float psum = 0.f;
       uint32_t pk[32];
+      if (fast) {
+        const float cm = cb - m_use;
 #pragma unroll
-      for (int c = 0; c < 64; c += 2) {
-        const float p0 = exp2f(__uint_as_float(c < 32 ? r0[c] : r1[c - 32]) - m_use);
-        const float p1 = exp2f(__uint_as_float(c < 32 ? r0[c + 1] : r1[c - 31]) - m_use);
-        psum += p0 + p1;
-        pk[c >> 1] = pack_bf16(p0, p1);
+        for (int c = 0; c < 64; c += 2) {
+          const float p0 = exp2f(fmaf(__uint_as_float(c < 32 ? r0[c] : r1[c - 32]), sl2, cm));
+          const float p1 = exp2f(fmaf(__uint_as_float(c < 32 ? r0[c + 1] : r1[c - 31]), sl2, cm));
+          psum += p0 + p1;
+          pk[c >> 1] = pack_bf16(p0, p1);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) {
+          const float p0 = exp2f(__uint_as_float(c < 32 ? r0[c] : r1[c - 32]) - m_use);
+          const float p1 = exp2f(__uint_as_float(c < 32 ? r0[c + 1] : r1[c - 31]) - m_use);
+          psum += p0 + p1;
+          pk[c >> 1] = pack_bf16(p0, p1);
+        }
       }
       l = l * corr + psum;
       m = m_new;
@@ -240,14 +268,18 @@ int flash_attention_launch(const TtbAttnArgs& a, cudaStream_t st) {
                           (uint64_t)a.T * a.ld, 64, FA_BM)) return -1;
   if (get_tensor_map_bf16(&mkv, a.qkv, (uint64_t)a.ld, (uint64_t)a.T, (uint64_t)a.nseq, (uint64_t)a.ld,
                           (uint64_t)a.T * a.ld, 64, FA_BN)) return -1;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(flash_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FaSmem::TOTAL);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(flash_attn)");
-    attr = true;
+  static int occ = 0;
+  if (!occ) {
+    const char* e = getenv("TTB_FA_OCC");       // CTAs per SM the kernel is compiled for (register cap): 2 (default) or 3
+    occ = (e && atoi(e) == 3) ? 3 : 2;
+    cudaError_t r = (occ == 3)
+        ? cudaFuncSetAttribute(flash_attn_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FaSmem::TOTAL)
+        : cudaFuncSetAttribute(flash_attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FaSmem::TOTAL);
+    if (r != cudaSuccess) { occ = 0; return check_cuda(r, "cudaFuncSetAttribute(flash_attn)"); }
   }
   dim3 grid((a.T + FA_BM - 1) / FA_BM, a.H, a.nseq);
-  flash_attn_tc_kernel<<<grid, FA_THREADS, FaSmem::TOTAL, st>>>(mq, mkv, a);
+  if (occ == 3) flash_attn_tc_kernel<3><<<grid, FA_THREADS, FaSmem::TOTAL, st>>>(mq, mkv, a);
+  else flash_attn_tc_kernel<2><<<grid, FA_THREADS, FaSmem::TOTAL, st>>>(mq, mkv, a);
   TTB_CHECK_LAUNCH("flash_attn_tc_kernel");
   return 0;
 }

@@ -115,7 +115,7 @@ struct GemmSmem {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
-                    int K, int taps, int pad, int a_batch_mul, GemmEpilogue ep) {
+                    int K, int taps, int pad, int a_batch_mul, int kb_per_split, GemmEpilogue ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using L = GemmSmem<BN, STAGES>;
@@ -130,7 +130,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const int m0 = blockIdx.y * BM;
   const int bz = blockIdx.z;
   const int kblocks_per_tap = K / BK;
-  const int num_kb = kblocks_per_tap * taps;
+  // split-K: grid.z enumerates K ranges of kb_per_split k-blocks (batch == 1); each split writes a raw partial
+  const int kb_total = kblocks_per_tap * taps;
+  const int kb_begin = kb_per_split > 0 ? bz * kb_per_split : 0;
+  const int num_kb = kb_per_split > 0 ? min(kb_per_split, kb_total - kb_begin) : kb_total;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -149,8 +152,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // ===== TMA producer =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kbi = 0; kbi < num_kb; ++kbi) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        const int kb = kb_begin + kbi;
         const int tap = kb / kblocks_per_tap;
         const int kk = (kb - tap * kblocks_per_tap) * BK;
         uint8_t* sa = smem + stage * L::STAGE_BYTES;
@@ -337,8 +341,15 @@ static int launch_tc(const TtbGemmArgs& g, const GemmEpilogue& ep, cudaStream_t 
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm)");
     attr_set = true;
   }
-  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.batch);
-  gemm_bf16_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, st>>>(ma, mb, g.M, g.N, g.K, g.taps, g.pad, bcast ? 0 : 1, ep);
+  int kb_per_split = 0, zdim = g.batch;
+  if (g.splitk > 1) {
+    const int kb_total = (g.K / BK) * g.taps;
+    kb_per_split = (kb_total + g.splitk - 1) / g.splitk;
+    zdim = (kb_total + kb_per_split - 1) / kb_per_split;     // every split owns >= 1 k-block
+  }
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, zdim);
+  gemm_bf16_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, st>>>(ma, mb, g.M, g.N, g.K, g.taps, g.pad,
+                                                                        (bcast || g.splitk > 1) ? 0 : 1, kb_per_split, ep);
   TTB_CHECK_LAUNCH("gemm_bf16_tc_kernel");
   return 0;
 }
@@ -362,6 +373,14 @@ extern "C" int ttb_gemm(const TtbGemmArgs* gp, void* stream) {
     const char* e = getenv("TTB_GEMM_IMPL");
     g_gemm_impl = (e && strcmp(e, "ref") == 0) ? 1 : 0;
   }
+  if (g.splitk > 1) {
+    // split-K writes raw fp32 partials [split, M, ldo] (consumed by ttb_residual_layernorm); no epilogue fusion
+    if (g.batch != 1 || g.act != TTB_ACT_NONE || !g.out_f32 || g.out_bf16 || g.bias || g.residual) {
+      set_error("ttb_gemm: splitk needs batch=1, no activation/bias/residual and an fp32 partial buffer");
+      return -1;
+    }
+    if (g_gemm_impl == 1 || g.force_ref) { set_error("ttb_gemm: splitk is not available in the SIMT checker"); return -1; }
+  }
   if (g_gemm_impl == 1 || g.force_ref) {
     dim3 block(128), grid((g.N + 127) / 128, g.M, g.batch);
     gemm_ref_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g.A), g.a_bstride, g.lda, g.rows,
@@ -371,6 +390,7 @@ extern "C" int ttb_gemm(const TtbGemmArgs* gp, void* stream) {
   }
   // tile choice: fill the 148 SMs; small-N / small-M problems use narrower tiles
   const long long tiles128 = (long long)((g.N + 127) / 128) * ((g.M + BM - 1) / BM) * g.batch;
+  if (g.tile_n == 32) return launch_tc<32, 4>(g, ep, st);
   if (g.tile_n == 64 || (g.tile_n == 0 && tiles128 < 148)) return launch_tc<64, 4>(g, ep, st);
   return launch_tc<128, 3>(g, ep, st);
 }

@@ -8,9 +8,10 @@ namespace ttb {
 // one block (256 threads) per row; D <= 4096; row cached in registers (up to 16 per thread)
 template <int MAXV>
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const float* __restrict__ x, int D, const float* __restrict__ g1, const float* __restrict__ b1,
+layernorm_kernel(const float* x, int D, const float* __restrict__ g1, const float* __restrict__ b1,
                  const float* __restrict__ g2, const float* __restrict__ b2, __nv_bfloat16* __restrict__ ob,
-                 float* __restrict__ of) {
+                 float* __restrict__ of, float* xw, const float* __restrict__ partials, int nsplit,
+                 long long split_stride, const float* __restrict__ rbias) {
   __shared__ float red[32];
   const long long row = blockIdx.x;
   const float* xr = x + row * D;
@@ -20,6 +21,12 @@ layernorm_kernel(const float* __restrict__ x, int D, const float* __restrict__ g
   for (int i = 0; i < MAXV; ++i) {
     int c = threadIdx.x + i * 256;
     v[i] = (c < D) ? xr[c] : 0.f;
+    if (xw && c < D) {          // fused residual update: x += bias + sum of split-K partials (fixed order)
+      float t = rbias ? rbias[c] : 0.f;
+      for (int sp = 0; sp < nsplit; ++sp) t += partials[sp * split_stride + row * D + c];
+      v[i] += t;
+      xw[row * D + c] = v[i];
+    }
     s += v[i];
   }
   float mean = block_sum(s, red) / D;
@@ -169,10 +176,23 @@ extern "C" int ttb_layernorm(const float* x, int M, int D, const float* g1, cons
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (M <= 0) return 0;
   auto ob = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-  if (D <= 1024) layernorm_kernel<4><<<M, 256, 0, st>>>(x, D, g1, b1, g2, b2, ob, out_f32);
-  else if (D <= 4096) layernorm_kernel<16><<<M, 256, 0, st>>>(x, D, g1, b1, g2, b2, ob, out_f32);
+  if (D <= 1024) layernorm_kernel<4><<<M, 256, 0, st>>>(x, D, g1, b1, g2, b2, ob, out_f32, nullptr, nullptr, 0, 0, nullptr);
+  else if (D <= 4096) layernorm_kernel<16><<<M, 256, 0, st>>>(x, D, g1, b1, g2, b2, ob, out_f32, nullptr, nullptr, 0, 0, nullptr);
   else { set_error("ttb_layernorm: D=%d > 4096", D); return -1; }
   TTB_CHECK_LAUNCH("layernorm_kernel");
+  return 0;
+}
+
+extern "C" int ttb_residual_layernorm(float* x, int M, int D, const float* partials, int nsplit, long long split_stride,
+                                      const float* bias, const float* g1, const float* b1, const float* g2,
+                                      const float* b2, void* out_bf16, float* out_f32, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (M <= 0) return 0;
+  auto ob = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  if (D <= 1024) layernorm_kernel<4><<<M, 256, 0, st>>>(x, D, g1, b1, g2, b2, ob, out_f32, x, partials, nsplit, split_stride, bias);
+  else if (D <= 4096) layernorm_kernel<16><<<M, 256, 0, st>>>(x, D, g1, b1, g2, b2, ob, out_f32, x, partials, nsplit, split_stride, bias);
+  else { set_error("ttb_residual_layernorm: D=%d > 4096", D); return -1; }
+  TTB_CHECK_LAUNCH("layernorm_kernel(residual)");
   return 0;
 }
 

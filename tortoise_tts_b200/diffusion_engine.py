@@ -169,8 +169,9 @@ class DiffusionEngine:
         self._gn(x, B, S, aw.gn_g, aw.gn_b, ws)
         lib.gemm(ws["a"], aw.wqkv, M=S, N=3 * C, K=C, bias=aw.bqkv, out_bf16=ws["qkv"], batch=B, a_bstride=S * C,
                  outb_bstride=S * 3 * C)
+        # T5 buckets saturate at max_distance = 64 (xtransformers.py:166-174): |j - i| >= 64 -> constant bias per side
         lib.attention(ws["qkv"], ws["o"], nseq=B, T=S, H=H, ld=3 * C, ldo=C, k_off=C, v_off=2 * C, scale=0.125,
-                      bias=aw.table(S))
+                      bias=aw.table(S), bias_sat=64)
         lib.gemm(ws["o"], aw.wproj, M=S, N=C, K=C, bias=aw.bproj, residual=x, out_f32=x, batch=B, a_bstride=S * C,
                  res_bstride=S * C, outf_bstride=S * C)
 

@@ -25,14 +25,14 @@ class GemmArgs(C.Structure):
                 ("lda", C.c_int), ("ldr", C.c_int), ("ldo", C.c_int), ("ldob", C.c_int),
                 ("rows", C.c_int), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
                 ("taps", C.c_int), ("pad", C.c_int), ("batch", C.c_int), ("act", C.c_int),
-                ("alpha", C.c_float), ("tile_n", C.c_int), ("force_ref", C.c_int)]
+                ("alpha", C.c_float), ("tile_n", C.c_int), ("force_ref", C.c_int), ("splitk", C.c_int)]
 
 
 class AttnArgs(C.Structure):
     _fields_ = [("qkv", C.c_void_p), ("out", C.c_void_p), ("bias", C.c_void_p),
                 ("nseq", C.c_int), ("T", C.c_int), ("H", C.c_int),
                 ("ld", C.c_int), ("ldo", C.c_int), ("k_off", C.c_int), ("v_off", C.c_int),
-                ("scale", C.c_float), ("causal", C.c_int)]
+                ("scale", C.c_float), ("causal", C.c_int), ("bias_sat", C.c_int)]
 
 
 class DiffStepArgs(C.Structure):
@@ -48,7 +48,7 @@ _lib = None
 # every symbol include/ttb.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "ttb_last_error", "ttb_version", "ttb_device_ok", "ttb_gemm", "ttb_layernorm", "ttb_rmsnorm", "ttb_groupnorm",
-    "ttb_attention", "ttb_ar_embed_step", "ttb_ar_decode_attention", "ttb_ar_store_prefix", "ttb_ar_sample",
+    "ttb_residual_layernorm", "ttb_attention", "ttb_ar_embed_step", "ttb_ar_decode_attention", "ttb_ar_store_prefix", "ttb_ar_sample",
     "ttb_ar_fix_codes", "ttb_embed", "ttb_clvp_rotary", "ttb_clvp_pool", "ttb_clvp_project",
     "ttb_timestep_embedding", "ttb_linear_small", "ttb_interp_nearest", "ttb_diffusion_step", "ttb_counter_add",
     "ttb_transpose_f32", "ttb_cast_pad_bf16", "ttb_broadcast_rows", "ttb_voc_conv1d", "ttb_voc_convt",
@@ -108,7 +108,7 @@ def _f32(t):
 # ------------------------------------------------------------------ wrappers
 def gemm(A, W, *, M, N, K, bias=None, residual=None, out_f32=None, out_bf16=None, lda=None, rows=None, batch=1,
          a_bstride=0, res_bstride=0, outf_bstride=0, outb_bstride=0, ldr=None, ldo=None, ldob=None, taps=1, pad=0,
-         act=ACT_NONE, alpha=1.0, tile_n=0, force_ref=False):
+         act=ACT_NONE, alpha=1.0, tile_n=0, force_ref=False, splitk=1):
     """See include/ttb.h ttb_gemm. A: bf16 [batch, rows, lda]; W: bf16 [N, taps*K]."""
     _bf(A), _bf(W), _f32(bias), _f32(residual), _f32(out_f32), _bf(out_bf16)
     n_out = N // 2 if act == ACT_GEGLU else N
@@ -122,13 +122,20 @@ def gemm(A, W, *, M, N, K, bias=None, residual=None, out_f32=None, out_bf16=None
     g.ldob = n_out if ldob is None else ldob
     g.rows = M if rows is None else rows
     g.M, g.N, g.K, g.taps, g.pad, g.batch, g.act = M, N, K, taps, pad, batch, act
-    g.alpha, g.tile_n, g.force_ref = alpha, tile_n, 1 if force_ref else 0
+    g.alpha, g.tile_n, g.force_ref, g.splitk = alpha, tile_n, 1 if force_ref else 0, splitk
     _chk(load().ttb_gemm(C.byref(g), _stream()), "ttb_gemm")
 
 
 def layernorm(x, M, D, g1, b1, g2=None, b2=None, out_bf16=None, out_f32=None):
     _chk(load().ttb_layernorm(_p(_f32(x)), M, D, _p(g1), _p(b1), _p(g2), _p(b2), _p(_bf(out_bf16)), _p(_f32(out_f32)),
                               _stream()), "ttb_layernorm")
+
+
+def residual_layernorm(x, M, D, partials, nsplit, split_stride, bias, g1, b1, g2=None, b2=None, out_bf16=None,
+                       out_f32=None):
+    _chk(load().ttb_residual_layernorm(_p(_f32(x)), M, D, _p(_f32(partials)), nsplit, C.c_longlong(split_stride),
+                                       _p(bias), _p(g1), _p(b1), _p(g2), _p(b2), _p(_bf(out_bf16)), _p(_f32(out_f32)),
+                                       _stream()), "ttb_residual_layernorm")
 
 
 def rmsnorm(x, M, D, g, out_bf16):
@@ -142,8 +149,9 @@ def groupnorm(x, B, S, Cc, groups, gamma, beta, partials, scale_shift=None, ss_b
                               _stream()), "ttb_groupnorm")
 
 
-def attention(qkv, out, *, nseq, T, H, ld, ldo, k_off, v_off, scale, causal=False, bias=None):
+def attention(qkv, out, *, nseq, T, H, ld, ldo, k_off, v_off, scale, causal=False, bias=None, bias_sat=0):
     a = AttnArgs()
+    a.bias_sat = int(bias_sat) if bias is not None else 0
     a.qkv, a.out, a.bias = _bf(qkv).data_ptr(), _bf(out).data_ptr(), _p(_f32(bias)).value or 0
     a.nseq, a.T, a.H, a.ld, a.ldo, a.k_off, a.v_off = nseq, T, H, ld, ldo, k_off, v_off
     a.scale, a.causal = scale, 1 if causal else 0
