@@ -67,6 +67,9 @@ CASES = [
     dict(M=77, N=200, K=1024, taps=3),               # diffusion out conv (N=200)
     dict(M=1882, N=24832, K=64, taps=3),             # UnivNet kernel predictor
     dict(M=130, N=192, K=64, act=2, out="both"),
+    dict(M=1872, N=1024, K=1024, taps=3, batch=2, tile_n=256, residual=True),   # 128x256 tiles
+    dict(M=3000, N=2304, K=768, out="bf16"),                                     # auto -> 128x256 (CLVP qkv shape)
+    dict(M=300, N=512, K=128, tile_n=256, act=1),
 ]
 
 

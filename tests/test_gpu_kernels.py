@@ -94,7 +94,8 @@ def test_attention(T, H, nseq, causal, use_bias):
     if causal:
         w = w.masked_fill(~torch.ones(T, T, dtype=torch.bool, device="cuda").tril(), float("-inf"))
     want = (torch.softmax(w, -1) @ v).transpose(1, 2).reshape(nseq * T, D)
-    err = (out.float() - want).abs().max().item()
+    # outputs are bf16: tolerance relative to the output scale (|v| reaches ~15 in the "big" case)
+    err = (out.float() - want).abs().max().item() / max(1.0, want.abs().max().item() / 4.0)
     report("attention T=%d causal=%d bias=%s" % (T, causal, use_bias), err)
     assert err < 0.03
 

@@ -151,7 +151,7 @@ TTB_DEVINL float dec_dot(const float* q, const uint4& kk) {
   return d;
 }
 
-__global__ void __launch_bounds__(DEC_THREADS)
+__global__ void __launch_bounds__(DEC_THREADS, 4)
 ar_decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ pk,
                       const __nv_bfloat16* __restrict__ pv, __nv_bfloat16* __restrict__ ck,
                       __nv_bfloat16* __restrict__ cv, const TtbArState* __restrict__ state, int B, int H, int P, int Nmax,
