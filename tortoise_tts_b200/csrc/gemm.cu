@@ -395,6 +395,8 @@ extern "C" int ttb_gemm(const TtbGemmArgs* gp, void* stream) {
   // large problems are L2-bandwidth bound with 128x128 tiles (64 flop/B at ~6.3 KB/clk of L2): 128x256 tiles raise the
   // intensity to 85 flop/B when the grid still covers most SMs
   const long long tiles256 = (long long)((g.N + 255) / 256) * ((g.M + BM - 1) / BM) * g.batch;
-  if (g.tile_n == 256 || (g.tile_n == 0 && tiles256 >= 110 && g.N % 256 == 0)) return launch_tc<256, 3>(g, ep, st);
+  // (measured on B200: 1 CTA/SM with 256-wide tiles is slower than 2 CTAs/SM with 128-wide ones, so only on request)
+  (void)tiles256;
+  if (g.tile_n == 256) return launch_tc<256, 3>(g, ep, st);
   return launch_tc<128, 3>(g, ep, st);
 }
