@@ -85,6 +85,15 @@ typedef struct TtbAttnArgs {
   int ld, ldo, k_off, v_off;
   float scale;          /* applied to q.k */
   int causal;
+  /* optional split form (used for the shared-prompt part of the AR decode attention): keys/values from a head-major
+   * cache bf16 [H, Tk, 64] shared by all sequences, result written as fp32 normalised rows + log2-sum-exp so that it
+   * can be merged with attention over another key range */
+  const void* kv;       /* K cache or NULL */
+  const void* kv_v;     /* V cache */
+  int kv_headmajor;     /* 1 = kv/kv_v are [H, Tk, 64] */
+  int Tk;               /* keys per sequence (0 = T) */
+  float* out_f32;       /* fp32 [nseq*T, ldo] (with lse) */
+  float* lse;           /* fp32 [nseq*T, H], log2 domain, or NULL */
   int bias_sat;         /* > 0: bias[h][r] == bias[h][-(T-1)] for r <= -bias_sat and == bias[h][T-1] for r >= bias_sat
                            (T5 buckets saturate at max_distance); lets far-from-diagonal tiles skip the table. 0 = unknown */
 } TtbAttnArgs;
@@ -106,7 +115,8 @@ int ttb_ar_embed_step(const int* codes, int ld_codes, const TtbArState* state, c
 /* One-query attention over [shared prefix | candidate KV] for every (candidate, head); appends the new K/V.
  * prefix_k/v: bf16 [H, P, 64]; cand_k/v: bf16 [B, H, Nmax, 64]; qkv bf16 [B, 3*H*64]. */
 int ttb_ar_decode_attention(const void* qkv, const void* prefix_k, const void* prefix_v, void* cand_k, void* cand_v,
-                            const TtbArState* state, int B, int H, int P, int Nmax, void* out, void* stream);
+                            const TtbArState* state, int B, int H, int P, int Nmax, void* out, float* scratch_o,
+                            float* scratch_lse, void* stream);   /* scratch: fp32 [B, H*64] and [B, H] */
 /* copy K/V of the prompt from a qkv buffer [P, 3*H*64] into the prefix cache [H, P, 64] */
 int ttb_ar_store_prefix(const void* qkv, int P, int H, void* prefix_k, void* prefix_v, void* stream);
 /* HF sample() step, fused: repetition penalty over the ids seen (incl. fake prompt ids 1 and 8192), temperature,

@@ -121,7 +121,7 @@ def ar_embed_step(codes, ld_codes, state, mel_emb, mel_pos, B, D, pos_mode, x):
     _v(x, (B, D), (D, 1)).copy_(mel_emb[tok] + mel_pos[j + 1 if pos_mode else j])
 
 
-def ar_decode_attention(qkv, pk, pv, ck, cv, state, B, H, P, Nmax, out):
+def ar_decode_attention(qkv, pk, pv, ck, cv, state, B, H, P, Nmax, out, scratch_o=None, scratch_lse=None):
     D = H * 64
     slot = int(state[0]) - 1
     r = _v(qkv, (B, 3 * D), (3 * D, 1))

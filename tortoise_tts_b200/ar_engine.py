@@ -129,6 +129,8 @@ class AREngine:
         st["x"] = torch.empty(B, D, dtype=torch.float32, device=dev)
         st["ws"] = self._alloc_trunk(B)
         st["hn"] = torch.empty(max(B, 1), D, dtype=torch.bfloat16, device=dev)
+        st["att_o"] = torch.zeros(B, D, dtype=torch.float32, device=dev)
+        st["att_lse"] = torch.zeros(B, H, dtype=torch.float32, device=dev)
         st["part_a"] = torch.zeros(max(self.SPLITK_PROJ, 2), B, D, dtype=torch.float32, device=dev)
         st["part_b"] = torch.zeros(max(self.SPLITK_PROJ2, 2), B, D, dtype=torch.float32, device=dev)
         st["logits"] = torch.empty(B, self.V, dtype=torch.float32, device=dev)
@@ -162,7 +164,7 @@ class AREngine:
                 lib.residual_layernorm(x, B, D, prev[0], prev[1], B * D, prev[2], lw["ln1_g"], lw["ln1_b"], out_bf16=ws["a"])
             lib.gemm(ws["a"], lw["wqkv"], M=B, N=3 * D, K=D, bias=lw["bqkv"], out_bf16=ws["qkv"], tile_n=32)
             lib.ar_decode_attention(ws["qkv"], st["pk"][l], st["pv"][l], st["ck"][l], st["cv"][l], st["state"], B, H, P,
-                                    Nmax, ws["o"])
+                                    Nmax, ws["o"], st["att_o"], st["att_lse"])
             lib.gemm(ws["o"], lw["wproj"], M=B, N=D, K=D, out_f32=pa, outf_bstride=B * D, tile_n=32, splitk=max(s1, 2))
             lib.residual_layernorm(x, B, D, pa, self._nsplit(kb, max(s1, 2)), B * D, lw["bproj"], lw["ln2_g"], lw["ln2_b"],
                                    out_bf16=ws["a"])

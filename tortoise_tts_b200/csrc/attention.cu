@@ -6,6 +6,7 @@
 //    for the GPT-2 sampler; memory-bound on the KV stream (HBM roofline), appends the new K/V.
 #include "common.cuh"
 #include "ttb_internal.h"
+#include <cstring>
 
 namespace ttb {
 
@@ -155,9 +156,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 4)
 ar_decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ pk,
                       const __nv_bfloat16* __restrict__ pv, __nv_bfloat16* __restrict__ ck,
                       __nv_bfloat16* __restrict__ cv, const TtbArState* __restrict__ state, int B, int H, int P, int Nmax,
-                      __nv_bfloat16* __restrict__ out) {
-  __shared__ __align__(16) __nv_bfloat16 spk[DEC_PT * 64];
-  __shared__ __align__(16) __nv_bfloat16 spv[DEC_PT * 64];
+                      const float* __restrict__ o_p, const float* __restrict__ lse_p, __nv_bfloat16* __restrict__ out) {
   const int h = blockIdx.x;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y * DEC_WARPS + w;
@@ -167,8 +166,6 @@ ar_decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16
   // decode step t (>= 1) feeds token t-1 whose K/V land in candidate slot t-1
   const int slot = state->step - 1;
   const int nc = slot + 1;                     // candidate entries incl. the new one
-  const __nv_bfloat16* pkb = pk + (long long)h * P * 64;
-  const __nv_bfloat16* pvb = pv + (long long)h * P * 64;
   __nv_bfloat16* ckb = ck + ((long long)(active ? b : 0) * H + h) * Nmax * 64;
   __nv_bfloat16* cvb = cv + ((long long)(active ? b : 0) * H + h) * Nmax * 64;
   float q[8];
@@ -184,33 +181,20 @@ ar_decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16
       reinterpret_cast<uint4*>((lane < 8 ? ckb : cvb) + (long long)slot * 64)[dch] = nv;
     }
   }
+  // ---- the shared-prompt part was computed on the tensor cores (flash_attn_tc_kernel over the prefix cache):
+  // normalised o_p (fp32) and lse_p (log2 domain) per (candidate, head). (m = lse_p, l = 1, acc = o_p) is an
+  // equivalent online-softmax state; only the psub == 0 stream carries it.
   DecState st;
   st.m = -INFINITY; st.l = 0.f;
 #pragma unroll
   for (int d = 0; d < 8; ++d) st.acc[d] = 0.f;
-  // ---- phase A: shared prefix, staged in shared memory
-  for (int p0 = 0; p0 < P; p0 += DEC_PT) {
-    __syncthreads();
-    const int np = min(DEC_PT, P - p0);
-    for (int i = threadIdx.x; i < DEC_PT * 8; i += DEC_THREADS) {
-      const int r = i >> 3, c = i & 7;
-      uint4 a = make_uint4(0, 0, 0, 0), v = make_uint4(0, 0, 0, 0);
-      if (r < np) {
-        a = reinterpret_cast<const uint4*>(pkb + (long long)(p0 + r) * 64)[c];
-        v = reinterpret_cast<const uint4*>(pvb + (long long)(p0 + r) * 64)[c];
-      }
-      reinterpret_cast<uint4*>(spk)[i] = a;
-      reinterpret_cast<uint4*>(spv)[i] = v;
-    }
-    __syncthreads();
-#pragma unroll 4
-    for (int r0 = 0; r0 < DEC_PT; r0 += 4) {
-      const int r = r0 + psub;
-      const uint4 kk = reinterpret_cast<const uint4*>(spk)[r * 8 + dch];
-      const uint4 vv = reinterpret_cast<const uint4*>(spv)[r * 8 + dch];
-      const float s = dec_dot(q, kk);
-      dec_update(st, s, r < np, vv);
-    }
+  if (active && psub == 0) {
+    st.m = lse_p[(long long)b * H + h];
+    st.l = 1.f;
+    const float4* op = reinterpret_cast<const float4*>(o_p + (long long)b * D + h * 64 + dch * 8);
+    const float4 a0 = op[0], a1 = op[1];
+    st.acc[0] = a0.x; st.acc[1] = a0.y; st.acc[2] = a0.z; st.acc[3] = a0.w;
+    st.acc[4] = a1.x; st.acc[5] = a1.y; st.acc[6] = a1.z; st.acc[7] = a1.w;
   }
   // ---- phase B: the candidate's own KV, streamed from global memory
   __syncwarp();
@@ -283,13 +267,22 @@ extern "C" int ttb_attention(const TtbAttnArgs* ap, void* stream) {
 
 extern "C" int ttb_ar_decode_attention(const void* qkv, const void* prefix_k, const void* prefix_v, void* cand_k,
                                        void* cand_v, const TtbArState* state, int B, int H, int P, int Nmax, void* out,
-                                       void* stream) {
+                                       float* scratch_o, float* scratch_lse, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // (1) shared prompt prefix: dense [B candidates x P keys] attention per head on the tensor cores
+  TtbAttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.qkv = qkv; a.nseq = 1; a.T = B; a.H = H; a.ld = 3 * H * 64; a.ldo = H * 64;
+  a.scale = 0.125f; a.kv = prefix_k; a.kv_v = prefix_v; a.kv_headmajor = 1; a.Tk = P;
+  a.out_f32 = scratch_o; a.lse = scratch_lse;
+  if (flash_attention_launch(a, st)) return -1;
+  // (2) every candidate's own KV stream (HBM-bound), continuing from the prefix state
   dim3 grid(H, (B + DEC_WARPS - 1) / DEC_WARPS);
   ar_decode_attn_kernel<<<grid, DEC_THREADS, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(prefix_k),
       reinterpret_cast<const __nv_bfloat16*>(prefix_v), reinterpret_cast<__nv_bfloat16*>(cand_k),
-      reinterpret_cast<__nv_bfloat16*>(cand_v), state, B, H, P, Nmax, reinterpret_cast<__nv_bfloat16*>(out));
+      reinterpret_cast<__nv_bfloat16*>(cand_v), state, B, H, P, Nmax, scratch_o, scratch_lse,
+      reinterpret_cast<__nv_bfloat16*>(out));
   TTB_CHECK_LAUNCH("ar_decode_attn_kernel");
   return 0;
 }

@@ -37,7 +37,8 @@ struct FaSmem {
 
 template <int MINB>
 __global__ void __launch_bounds__(FA_THREADS, MINB)
-flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, TtbAttnArgs a) {
+flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                     const __grid_constant__ CUtensorMap map_v, TtbAttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FaSmem::BAR_OFF);
@@ -52,13 +53,20 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * FA_BM, h = blockIdx.y, seq = blockIdx.z;
-  const int T = a.T;
+  const int Tq = a.T;                          // queries per sequence
+  const int T = a.Tk > 0 ? a.Tk : a.T;         // keys per sequence (bias / causal need Tk == T)
   const int kv_end = a.causal ? min(T, q0 + FA_BM) : T;
+  // KV addressing: packed qkv rows (k_off/v_off + 64*h columns, sequence = 3rd coordinate) or a head-major cache
+  // [H][Tk][64] shared by every sequence (kv_headmajor): head = 3rd coordinate.
+  const int kc0 = a.kv_headmajor ? 0 : a.k_off + h * 64;
+  const int vc0 = a.kv_headmajor ? 0 : a.v_off + h * 64;
+  const int kvc2 = a.kv_headmajor ? h : seq;
   const int ntiles = (kv_end + FA_BN - 1) / FA_BN;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_q);
-    tma_prefetch_desc(&map_kv);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
     mbar_init(q_full, 1);
     for (int s = 0; s < FA_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     mbar_init(s_full, 1);
@@ -84,8 +92,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         uint8_t* sk = smem + FaSmem::KV_OFF + stage * (FaSmem::K_BYTES + FaSmem::V_BYTES);
         uint8_t* sv = sk + FaSmem::K_BYTES;
         mbar_arrive_expect_tx(&kv_full[stage], FaSmem::K_BYTES + FaSmem::V_BYTES);
-        tma_load_3d(sk, &map_kv, &kv_full[stage], a.k_off + h * 64, j * FA_BN, seq);
-        tma_load_3d(sv, &map_kv, &kv_full[stage], a.v_off + h * 64, j * FA_BN, seq);
+        tma_load_3d(sk, &map_k, &kv_full[stage], kc0, j * FA_BN, kvc2);
+        tma_load_3d(sv, &map_v, &kv_full[stage], vc0, j * FA_BN, kvc2);
         if (++stage == FA_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -234,9 +242,17 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       for (int d = 0; d < 32; ++d) { o[d] = __uint_as_float(t0[d]); o[d + 32] = __uint_as_float(t1[d]); }
     }
     tc_fence_before();
-    if (qi < T) {
+    if (qi < Tq && a.lse) {
+      // partial-attention mode: normalised O in fp32 + log2-sum-exp, to be merged with another key range
       const float inv = 1.0f / l;
-      __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + ((long long)seq * T + qi) * a.ldo + h * 64;
+      float* op = a.out_f32 + ((long long)seq * Tq + qi) * a.ldo + h * 64;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        reinterpret_cast<float4*>(op)[i] = make_float4(o[4 * i] * inv, o[4 * i + 1] * inv, o[4 * i + 2] * inv, o[4 * i + 3] * inv);
+      a.lse[((long long)seq * Tq + qi) * a.H + h] = m + log2f(l);
+    } else if (qi < Tq) {
+      const float inv = 1.0f / l;
+      __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + ((long long)seq * Tq + qi) * a.ldo + h * 64;
       uint4* o4 = reinterpret_cast<uint4*>(op);
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -259,15 +275,25 @@ bool flash_attention_supported(const TtbAttnArgs& a) {
     g_fa_mode = (e && strcmp(e, "simt") == 0) ? 0 : 1;
   }
   if (!g_fa_mode) return false;
+  if (a.kv || a.lse) return true;      // split Q / KV tensors and LSE output exist only in the tcgen05 kernel
   return a.T >= 64 && (a.ld % 8) == 0;
 }
 
 int flash_attention_launch(const TtbAttnArgs& a, cudaStream_t st) {
-  CUtensorMap mq, mkv;
+  CUtensorMap mq, mk, mv;
   if (get_tensor_map_bf16(&mq, a.qkv, (uint64_t)a.ld, (uint64_t)a.T, (uint64_t)a.nseq, (uint64_t)a.ld,
                           (uint64_t)a.T * a.ld, 64, FA_BM)) return -1;
-  if (get_tensor_map_bf16(&mkv, a.qkv, (uint64_t)a.ld, (uint64_t)a.T, (uint64_t)a.nseq, (uint64_t)a.ld,
-                          (uint64_t)a.T * a.ld, 64, FA_BN)) return -1;
+  if (a.kv_headmajor) {
+    if (!a.kv || !a.kv_v || a.Tk <= 0 || a.causal || a.bias) { set_error("flash attention: bad head-major KV arguments"); return -1; }
+    if (get_tensor_map_bf16(&mk, a.kv, 64, (uint64_t)a.Tk, (uint64_t)a.H, 64, (uint64_t)a.Tk * 64, 64, FA_BN)) return -1;
+    if (get_tensor_map_bf16(&mv, a.kv_v, 64, (uint64_t)a.Tk, (uint64_t)a.H, 64, (uint64_t)a.Tk * 64, 64, FA_BN)) return -1;
+  } else {
+    if (a.Tk > 0 && a.Tk != a.T) { set_error("flash attention: Tk != T needs the head-major KV form"); return -1; }
+    if (get_tensor_map_bf16(&mk, a.qkv, (uint64_t)a.ld, (uint64_t)a.T, (uint64_t)a.nseq, (uint64_t)a.ld,
+                            (uint64_t)a.T * a.ld, 64, FA_BN)) return -1;
+    mv = mk;
+  }
+  if (a.lse && !a.out_f32) { set_error("flash attention: lse output needs out_f32"); return -1; }
   static int occ = 0;
   if (!occ) {
     const char* e = getenv("TTB_FA_OCC");       // CTAs per SM the kernel is compiled for (register cap): 2 (default) or 3
@@ -278,8 +304,8 @@ int flash_attention_launch(const TtbAttnArgs& a, cudaStream_t st) {
     if (r != cudaSuccess) { occ = 0; return check_cuda(r, "cudaFuncSetAttribute(flash_attn)"); }
   }
   dim3 grid((a.T + FA_BM - 1) / FA_BM, a.H, a.nseq);
-  if (occ == 3) flash_attn_tc_kernel<3><<<grid, FA_THREADS, FaSmem::TOTAL, st>>>(mq, mkv, a);
-  else flash_attn_tc_kernel<2><<<grid, FA_THREADS, FaSmem::TOTAL, st>>>(mq, mkv, a);
+  if (occ == 3) flash_attn_tc_kernel<3><<<grid, FA_THREADS, FaSmem::TOTAL, st>>>(mq, mk, mv, a);
+  else flash_attn_tc_kernel<2><<<grid, FA_THREADS, FaSmem::TOTAL, st>>>(mq, mk, mv, a);
   TTB_CHECK_LAUNCH("flash_attn_tc_kernel");
   return 0;
 }

@@ -32,7 +32,9 @@ class AttnArgs(C.Structure):
     _fields_ = [("qkv", C.c_void_p), ("out", C.c_void_p), ("bias", C.c_void_p),
                 ("nseq", C.c_int), ("T", C.c_int), ("H", C.c_int),
                 ("ld", C.c_int), ("ldo", C.c_int), ("k_off", C.c_int), ("v_off", C.c_int),
-                ("scale", C.c_float), ("causal", C.c_int), ("bias_sat", C.c_int)]
+                ("scale", C.c_float), ("causal", C.c_int),
+                ("kv", C.c_void_p), ("kv_v", C.c_void_p), ("kv_headmajor", C.c_int), ("Tk", C.c_int),
+                ("out_f32", C.c_void_p), ("lse", C.c_void_p), ("bias_sat", C.c_int)]
 
 
 class DiffStepArgs(C.Structure):
@@ -163,9 +165,10 @@ def ar_embed_step(codes, ld_codes, state, mel_emb, mel_pos, B, D, pos_mode, x):
                                   _stream()), "ttb_ar_embed_step")
 
 
-def ar_decode_attention(qkv, pk, pv, ck, cv, state, B, H, P, Nmax, out):
+def ar_decode_attention(qkv, pk, pv, ck, cv, state, B, H, P, Nmax, out, scratch_o, scratch_lse):
     _chk(load().ttb_ar_decode_attention(_p(_bf(qkv)), _p(_bf(pk)), _p(_bf(pv)), _p(_bf(ck)), _p(_bf(cv)), _p(state),
-                                        B, H, P, Nmax, _p(_bf(out)), _stream()), "ttb_ar_decode_attention")
+                                        B, H, P, Nmax, _p(_bf(out)), _p(_f32(scratch_o)), _p(_f32(scratch_lse)),
+                                        _stream()), "ttb_ar_decode_attention")
 
 
 def ar_store_prefix(qkv, P, H, pk, pv):
