@@ -198,21 +198,53 @@ ar_decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16
   }
   // ---- phase B: the candidate's own KV, streamed from global memory
   __syncwarp();
+  // Software-pipelined: the loads of batch i+1 (8 positions: 2 K + 2 V 16-byte loads per lane) are issued before the
+  // math of batch i, so every warp keeps 4 KB in flight continuously instead of alternating load / compute phases.
   if (active) {
-    for (int j0 = 0; j0 < nc; j0 += 16) {
-      uint4 kk[4], vv[4];
+    constexpr int U = 2;
+    uint4 kk[U], vv[U], kn[U], vn[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int j = j0 + u * 4 + psub;
+    for (int u = 0; u < U; ++u) {
+      const int j = u * 4 + psub;
+      const bool ok = j < nc;
+      kk[u] = ok ? reinterpret_cast<const uint4*>(ckb + (long long)j * 64)[dch] : make_uint4(0, 0, 0, 0);
+      vv[u] = ok ? reinterpret_cast<const uint4*>(cvb + (long long)j * 64)[dch] : make_uint4(0, 0, 0, 0);
+    }
+    for (int j0 = 0; j0 < nc; j0 += 4 * U) {
+      const int jn = j0 + 4 * U;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = jn + u * 4 + psub;
         const bool ok = j < nc;
-        kk[u] = ok ? reinterpret_cast<const uint4*>(ckb + (long long)j * 64)[dch] : make_uint4(0, 0, 0, 0);
-        vv[u] = ok ? reinterpret_cast<const uint4*>(cvb + (long long)j * 64)[dch] : make_uint4(0, 0, 0, 0);
+        kn[u] = ok ? reinterpret_cast<const uint4*>(ckb + (long long)j * 64)[dch] : make_uint4(0, 0, 0, 0);
+        vn[u] = ok ? reinterpret_cast<const uint4*>(cvb + (long long)j * 64)[dch] : make_uint4(0, 0, 0, 0);
+      }
+      // one shared running-max update for the batch (fewer dependent EX2 than per-position updates)
+      float s[U];
+      float bm = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        s[u] = dec_dot(q, kk[u]);
+        s[u] = (j0 + u * 4 + psub < nc) ? s[u] : -INFINITY;
+        bm = fmaxf(bm, s[u]);
+      }
+      const float m_new = fmaxf(st.m, bm);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float corr = exp2f(st.m - m_use);
+      st.m = m_new;
+      st.l *= corr;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) st.acc[d] *= corr;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float p = exp2f(s[u] - m_use);
+        st.l += p;
+        const float2 f0 = unpack_bf16(vv[u].x), f1 = unpack_bf16(vv[u].y), f2 = unpack_bf16(vv[u].z), f3 = unpack_bf16(vv[u].w);
+        st.acc[0] += p * f0.x; st.acc[1] += p * f0.y; st.acc[2] += p * f1.x; st.acc[3] += p * f1.y;
+        st.acc[4] += p * f2.x; st.acc[5] += p * f2.y; st.acc[6] += p * f3.x; st.acc[7] += p * f3.y;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float s = dec_dot(q, kk[u]);
-        dec_update(st, s, j0 + u * 4 + psub < nc, vv[u]);
-      }
+      for (int u = 0; u < U; ++u) { kk[u] = kn[u]; vv[u] = vn[u]; }
     }
   }
   // ---- merge the 4 position sub-streams (lanes differing in bits 3,4), then normalise
