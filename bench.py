@@ -127,8 +127,8 @@ def kernel_probes(tts, cfg, n_mel, B, P):
     o2 = torch.empty(B, D, device=dev, dtype=torch.bfloat16)
     state = torch.zeros(64, dtype=torch.int32, device=dev)
     state[0] = n_mel // 2
-    so = torch.zeros(B, D, device=dev)
-    sl = torch.zeros(B, Hh, device=dev)
+    so = torch.zeros(2, B, D, device=dev)
+    sl = torch.zeros(2, B, Hh, device=dev)
     ms = timeit(lambda: lib.ar_decode_attention(qkv2, pk, pv, ck, cv, state, B, Hh, P, Nmax, o2, so, sl), flush=flush)
     nbytes = B * Hh * (n_mel // 2) * 64 * 2 * 2 + Hh * P * 64 * 2 * 2   # candidate K+V (bf16) + shared prefix once
     out.append(dict(kernel="AR decode attention (B=%d, ctx=%d+%d)" % (B, P, n_mel // 2), bound="hbm", ms=ms,

@@ -116,7 +116,7 @@ int ttb_ar_embed_step(const int* codes, int ld_codes, const TtbArState* state, c
  * prefix_k/v: bf16 [H, P, 64]; cand_k/v: bf16 [B, H, Nmax, 64]; qkv bf16 [B, 3*H*64]. */
 int ttb_ar_decode_attention(const void* qkv, const void* prefix_k, const void* prefix_v, void* cand_k, void* cand_v,
                             const TtbArState* state, int B, int H, int P, int Nmax, void* out, float* scratch_o,
-                            float* scratch_lse, void* stream);   /* scratch: fp32 [B, H*64] and [B, H] */
+                            float* scratch_lse, void* stream);   /* scratch: fp32 [2, B, H*64] and [2, B, H] */
 /* copy K/V of the prompt from a qkv buffer [P, 3*H*64] into the prefix cache [H, P, 64] */
 int ttb_ar_store_prefix(const void* qkv, int P, int H, void* prefix_k, void* prefix_v, void* stream);
 /* HF sample() step, fused: repetition penalty over the ids seen (incl. fake prompt ids 1 and 8192), temperature,

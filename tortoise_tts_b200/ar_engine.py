@@ -129,8 +129,8 @@ class AREngine:
         st["x"] = torch.empty(B, D, dtype=torch.float32, device=dev)
         st["ws"] = self._alloc_trunk(B)
         st["hn"] = torch.empty(max(B, 1), D, dtype=torch.bfloat16, device=dev)
-        st["att_o"] = torch.zeros(B, D, dtype=torch.float32, device=dev)
-        st["att_lse"] = torch.zeros(B, H, dtype=torch.float32, device=dev)
+        st["att_o"] = torch.zeros(2, B, D, dtype=torch.float32, device=dev)      # [prefix | candidate] partial rows
+        st["att_lse"] = torch.zeros(2, B, H, dtype=torch.float32, device=dev)
         st["part_a"] = torch.zeros(max(self.SPLITK_PROJ, 2), B, D, dtype=torch.float32, device=dev)
         st["part_b"] = torch.zeros(max(self.SPLITK_PROJ2, 2), B, D, dtype=torch.float32, device=dev)
         st["logits"] = torch.empty(B, self.V, dtype=torch.float32, device=dev)

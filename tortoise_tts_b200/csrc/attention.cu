@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 4)
 ar_decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ pk,
                       const __nv_bfloat16* __restrict__ pv, __nv_bfloat16* __restrict__ ck,
                       __nv_bfloat16* __restrict__ cv, const TtbArState* __restrict__ state, int B, int H, int P, int Nmax,
-                      const float* __restrict__ o_p, const float* __restrict__ lse_p, __nv_bfloat16* __restrict__ out) {
+                      float* __restrict__ o_c, float* __restrict__ lse_c) {
   const int h = blockIdx.x;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y * DEC_WARPS + w;
@@ -181,21 +181,13 @@ ar_decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16
       reinterpret_cast<uint4*>((lane < 8 ? ckb : cvb) + (long long)slot * 64)[dch] = nv;
     }
   }
-  // ---- the shared-prompt part was computed on the tensor cores (flash_attn_tc_kernel over the prefix cache):
-  // normalised o_p (fp32) and lse_p (log2 domain) per (candidate, head). (m = lse_p, l = 1, acc = o_p) is an
-  // equivalent online-softmax state; only the psub == 0 stream carries it.
+  // The shared-prompt part of the context is handled concurrently on the tensor cores (flash_attn_tc_kernel over the
+  // prefix cache, forked onto a side stream by the host wrapper); this kernel covers the candidate's own keys and
+  // emits a partial (normalised row, log2-sum-exp) that ar_attn_merge_kernel combines with the prefix partial.
   DecState st;
   st.m = -INFINITY; st.l = 0.f;
 #pragma unroll
   for (int d = 0; d < 8; ++d) st.acc[d] = 0.f;
-  if (active && psub == 0) {
-    st.m = lse_p[(long long)b * H + h];
-    st.l = 1.f;
-    const float4* op = reinterpret_cast<const float4*>(o_p + (long long)b * D + h * 64 + dch * 8);
-    const float4 a0 = op[0], a1 = op[1];
-    st.acc[0] = a0.x; st.acc[1] = a0.y; st.acc[2] = a0.z; st.acc[3] = a0.w;
-    st.acc[4] = a1.x; st.acc[5] = a1.y; st.acc[6] = a1.z; st.acc[7] = a1.w;
-  }
   // ---- phase B: the candidate's own KV, streamed from global memory
   __syncwarp();
   // Software-pipelined: the loads of batch i+1 (8 positions: 2 K + 2 V 16-byte loads per lane) are issued before the
@@ -264,11 +256,32 @@ ar_decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16
     st.m = m_new;
   }
   if (active && psub == 0) {
+    // partial result over the candidate's own keys: normalised fp32 row + log2-sum-exp (merged with the prefix part)
     const float inv = 1.0f / st.l;
-    uint4 o = make_uint4(pack_bf16(st.acc[0] * inv, st.acc[1] * inv), pack_bf16(st.acc[2] * inv, st.acc[3] * inv),
-                         pack_bf16(st.acc[4] * inv, st.acc[5] * inv), pack_bf16(st.acc[6] * inv, st.acc[7] * inv));
-    reinterpret_cast<uint4*>(out + (long long)b * D + h * 64)[dch] = o;
+    float4* op = reinterpret_cast<float4*>(o_c + (long long)b * D + h * 64 + dch * 8);
+    op[0] = make_float4(st.acc[0] * inv, st.acc[1] * inv, st.acc[2] * inv, st.acc[3] * inv);
+    op[1] = make_float4(st.acc[4] * inv, st.acc[5] * inv, st.acc[6] * inv, st.acc[7] * inv);
+    if (dch == 0) lse_c[(long long)b * H + h] = st.m + log2f(st.l);
   }
+}
+
+// out = softmax-merge of two partial attentions over disjoint key ranges: (o_p, lse_p) and (o_c, lse_c)
+__global__ void ar_attn_merge_kernel(const float* __restrict__ o_p, const float* __restrict__ lse_p,
+                                     const float* __restrict__ o_c, const float* __restrict__ lse_c, int B, int H,
+                                     __nv_bfloat16* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over B * H * 16 (4 dims each)
+  if (i >= (long long)B * H * 16) return;
+  const long long bh = i >> 4;
+  const int c = (int)(i & 15) * 4;
+  const float lp = lse_p[bh], lc = lse_c[bh];
+  const float mx = fmaxf(lp, lc);
+  const float wp = exp2f(lp - mx), wc = exp2f(lc - mx);
+  const float inv = 1.0f / (wp + wc);
+  const float4 a = *reinterpret_cast<const float4*>(o_p + bh * 64 + c);
+  const float4 d = *reinterpret_cast<const float4*>(o_c + bh * 64 + c);
+  uint2 o = make_uint2(pack_bf16((a.x * wp + d.x * wc) * inv, (a.y * wp + d.y * wc) * inv),
+                       pack_bf16((a.z * wp + d.z * wc) * inv, (a.w * wp + d.w * wc) * inv));
+  *reinterpret_cast<uint2*>(out + bh * 64 + c) = o;
 }
 
 __global__ void ar_store_prefix_kernel(const __nv_bfloat16* __restrict__ qkv, int P, int H, __nv_bfloat16* __restrict__ pk,
@@ -297,25 +310,55 @@ extern "C" int ttb_attention(const TtbAttnArgs* ap, void* stream) {
   return 0;
 }
 
+namespace {
+struct ForkJoin {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int init() {
+    if (side) return 0;
+    if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) return -1;
+    if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return -1;
+    if (cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess) return -1;
+    return 0;
+  }
+};
+ForkJoin g_fj;
+}  // namespace
+
 extern "C" int ttb_ar_decode_attention(const void* qkv, const void* prefix_k, const void* prefix_v, void* cand_k,
                                        void* cand_v, const TtbArState* state, int B, int H, int P, int Nmax, void* out,
                                        float* scratch_o, float* scratch_lse, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // (1) shared prompt prefix: dense [B candidates x P keys] attention per head on the tensor cores
+  if (g_fj.init()) { set_error("ttb_ar_decode_attention: cannot create the side stream"); return -2; }
+  float* o_p = scratch_o;
+  float* o_c = scratch_o + (long long)B * H * 64;
+  float* lse_p = scratch_lse;
+  float* lse_c = scratch_lse + (long long)B * H;
+  // fork: (1) shared prompt prefix = dense [B candidates x P keys] attention per head on the tensor cores (side stream;
+  // latency-bound, 2x16 CTAs) runs concurrently with (2) the HBM-bound stream over every candidate's own KV.
+  cudaError_t e = cudaEventRecord(g_fj.fork, st);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(g_fj.side, g_fj.fork, 0);
+  if (e != cudaSuccess) return check_cuda(e, "decode attention fork");
   TtbAttnArgs a;
   memset(&a, 0, sizeof(a));
   a.qkv = qkv; a.nseq = 1; a.T = B; a.H = H; a.ld = 3 * H * 64; a.ldo = H * 64;
   a.scale = 0.125f; a.kv = prefix_k; a.kv_v = prefix_v; a.kv_headmajor = 1; a.Tk = P;
-  a.out_f32 = scratch_o; a.lse = scratch_lse;
-  if (flash_attention_launch(a, st)) return -1;
-  // (2) every candidate's own KV stream (HBM-bound), continuing from the prefix state
+  a.out_f32 = o_p; a.lse = lse_p;
+  if (flash_attention_launch(a, g_fj.side)) return -1;
   dim3 grid(H, (B + DEC_WARPS - 1) / DEC_WARPS);
   ar_decode_attn_kernel<<<grid, DEC_THREADS, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(prefix_k),
       reinterpret_cast<const __nv_bfloat16*>(prefix_v), reinterpret_cast<__nv_bfloat16*>(cand_k),
-      reinterpret_cast<__nv_bfloat16*>(cand_v), state, B, H, P, Nmax, scratch_o, scratch_lse,
-      reinterpret_cast<__nv_bfloat16*>(out));
+      reinterpret_cast<__nv_bfloat16*>(cand_v), state, B, H, P, Nmax, o_c, lse_c);
   TTB_CHECK_LAUNCH("ar_decode_attn_kernel");
+  // join, then merge the two partials
+  e = cudaEventRecord(g_fj.join, g_fj.side);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(st, g_fj.join, 0);
+  if (e != cudaSuccess) return check_cuda(e, "decode attention join");
+  const long long n = (long long)B * H * 16;
+  ar_attn_merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(o_p, lse_p, o_c, lse_c, B, H,
+                                                                   reinterpret_cast<__nv_bfloat16*>(out));
+  TTB_CHECK_LAUNCH("ar_attn_merge_kernel");
   return 0;
 }
 

@@ -166,8 +166,10 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       tmem_ld_wait();
       float mx = -INFINITY;
       if (fast) {
+        float mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // 4 independent chains (ILP)
 #pragma unroll
-        for (int c = 0; c < 32; ++c) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[c]), __uint_as_float(r1[c])));
+        for (int c = 0; c < 32; ++c) mq[c & 3] = fmaxf(mq[c & 3], fmaxf(__uint_as_float(r0[c]), __uint_as_float(r1[c])));
+        mx = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3]));
         mx = fmaf(mx, sl2, cb);
       } else {
         const int klim = min(T - k0, a.causal ? (qi - k0 + 1) : FA_BN);   // keys c < klim are visible to this row
@@ -202,13 +204,15 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       uint32_t pk[32];
       if (fast) {
         const float cm = cb - m_use;
+        float ps[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < 64; c += 2) {
           const float p0 = exp2f(fmaf(__uint_as_float(c < 32 ? r0[c] : r1[c - 32]), sl2, cm));
           const float p1 = exp2f(fmaf(__uint_as_float(c < 32 ? r0[c + 1] : r1[c - 31]), sl2, cm));
-          psum += p0 + p1;
+          ps[(c >> 1) & 3] += p0 + p1;
           pk[c >> 1] = pack_bf16(p0, p1);
         }
+        psum = (ps[0] + ps[1]) + (ps[2] + ps[3]);
       } else {
 #pragma unroll
         for (int c = 0; c < 64; c += 2) {
