@@ -356,6 +356,55 @@ static int launch_tc(const TtbGemmArgs& g, const GemmEpilogue& ep, cudaStream_t 
 
 }  // namespace ttb
 
+#include "gemm_persist.cuh"
+
+namespace ttb {
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int PSTAGES>
+static int launch_persistent(const TtbGemmArgs& g, const GemmEpilogue& ep, cudaStream_t st) {
+  CUtensorMap ma, mb;
+  const bool bcast = (g.batch == 1) || (g.a_bstride == 0);
+  const uint64_t a_d2 = bcast ? 1 : (uint64_t)g.batch;
+  const uint64_t a_s2 = bcast ? (uint64_t)g.rows * g.lda : (uint64_t)g.a_bstride;
+  if (get_tensor_map_bf16(&ma, g.A, (uint64_t)g.K, (uint64_t)g.rows, a_d2, (uint64_t)g.lda, a_s2, BK, BM)) return -1;
+  if (get_tensor_map_bf16(&mb, g.W, (uint64_t)g.K * g.taps, (uint64_t)g.N, 1, (uint64_t)g.K * g.taps,
+                          (uint64_t)g.K * g.taps * g.N, BK, BN)) return -1;
+  using L = GemmPSmem<BN, PSTAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_persistent_kernel<BN, PSTAGES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm persistent)");
+    attr_set = true;
+  }
+  int kb_per_split = 0, zdim = g.batch;
+  if (g.splitk > 1) {
+    const int kb_total = (g.K / BK) * g.taps;
+    kb_per_split = (kb_total + g.splitk - 1) / g.splitk;
+    zdim = (kb_total + kb_per_split - 1) / kb_per_split;
+  }
+  const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
+  const long long total = (long long)m_tiles * n_tiles * zdim;
+  const int grid = (int)(total < num_sms() ? total : num_sms());
+  gemm_bf16_tc_persistent_kernel<BN, PSTAGES><<<grid, GEMM_THREADS, L::TOTAL, st>>>(
+      ma, mb, g.M, g.N, g.K, g.taps, g.pad, (bcast || g.splitk > 1) ? 0 : 1, kb_per_split, m_tiles, n_tiles, zdim, ep);
+  TTB_CHECK_LAUNCH("gemm_bf16_tc_persistent_kernel");
+  return 0;
+}
+
+}  // namespace ttb
+
 using namespace ttb;
 
 extern "C" int ttb_gemm(const TtbGemmArgs* gp, void* stream) {
@@ -390,6 +439,13 @@ extern "C" int ttb_gemm(const TtbGemmArgs* gp, void* stream) {
   }
   // tile choice: fill the 148 SMs; small-N / small-M problems use narrower tiles
   const long long tiles128 = (long long)((g.N + 127) / 128) * ((g.M + BM - 1) / BM) * g.batch;
+  static int persist = -1;   // TTB_GEMM_PERSIST=0 selects the one-tile-per-CTA kernels (A/B comparison)
+  if (persist < 0) { const char* e = getenv("TTB_GEMM_PERSIST"); persist = (e && atoi(e) == 0) ? 0 : 1; }
+  if (persist && g.tile_n != 256) {
+    if (g.tile_n == 32) return launch_persistent<32, 8>(g, ep, st);
+    if (g.tile_n == 64 || (g.tile_n == 0 && tiles128 < 148)) return launch_persistent<64, 8>(g, ep, st);
+    return launch_persistent<128, 6>(g, ep, st);
+  }
   if (g.tile_n == 32) return launch_tc<32, 4>(g, ep, st);
   if (g.tile_n == 64 || (g.tile_n == 0 && tiles128 < 148)) return launch_tc<64, 4>(g, ep, st);
   // large problems are L2-bandwidth bound with 128x128 tiles (64 flop/B at ~6.3 KB/clk of L2): 128x256 tiles raise the

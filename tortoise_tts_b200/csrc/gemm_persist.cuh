@@ -1,0 +1,216 @@
+// Persistent variant of the tcgen05 GEMM (included by gemm.cu after GemmEpilogue / BM / BK are defined).
+//
+// One CTA per SM loops over output tiles (tile id -> m fastest, then n, then batch/split), so that
+//   * the TMA -> MMA pipeline (PSTAGES deep) never drains between tiles,
+//   * the accumulator is double-buffered in TMEM (2 x BN columns): the epilogue of tile t overlaps the MMAs of t+1,
+//   * barrier init / TMEM allocation / descriptor prefetch are paid once per CTA instead of once per tile.
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue.
+#pragma once
+
+namespace ttb {
+
+template <int BN, int PSTAGES>
+struct GemmPSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = PSTAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * PSTAGES + 4) * 8 + 16 + 1024;
+};
+
+// epilogue of one 32-column chunk held in registers (thread = one output row)
+TTB_DEVINL void gemm_epilogue_chunk(const uint32_t* r, int nb, int N, const GemmEpilogue& ep, const float* res_row,
+                                    float* of_row, __nv_bfloat16* ob_row) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float x = __uint_as_float(r[j]) * ep.alpha;
+    if (ep.bias && nb + j < N) x += __ldg(ep.bias + nb + j);
+    v[j] = x;
+  }
+  if (ep.act == TTB_ACT_GEGLU) {
+    float o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf(v[2 * j + 1]);
+    const int ob = nb >> 1;
+    if (ob_row) {
+      if (nb + 32 <= N) {
+        uint4* dst = reinterpret_cast<uint4*>(ob_row + ob);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          dst[j] = make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
+                              pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
+      } else {
+        for (int j = 0; j < 16 && nb + 2 * j < N; ++j) ob_row[ob + j] = __float2bfloat16(o[j]);
+      }
+    }
+    if (of_row) for (int j = 0; j < 16 && nb + 2 * j < N; ++j) of_row[ob + j] = o[j];
+    return;
+  }
+  if (ep.act == TTB_ACT_GELU_NEW) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_new(v[j]);
+  } else if (ep.act == TTB_ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
+  } else if (ep.act == TTB_ACT_LRELU02) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = leaky(v[j], 0.2f);
+  }
+  const bool full = (nb + 32 <= N);
+  if (res_row) {
+    if (full && ((ep.ldr & 3) == 0)) {
+      const float4* rp = reinterpret_cast<const float4*>(res_row + nb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 t = rp[j];
+        v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+      }
+    } else {
+      for (int j = 0; j < 32 && nb + j < N; ++j) v[j] += res_row[nb + j];
+    }
+  }
+  if (of_row) {
+    if (full && ((ep.ldo & 3) == 0)) {
+      float4* dst = reinterpret_cast<float4*>(of_row + nb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+      for (int j = 0; j < 32 && nb + j < N; ++j) of_row[nb + j] = v[j];
+    }
+  }
+  if (ob_row) {
+    if (full && ((ep.ldob & 7) == 0)) {
+      uint4* dst = reinterpret_cast<uint4*>(ob_row + nb);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                            pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+    } else {
+      for (int j = 0; j < 32 && nb + j < N; ++j) ob_row[nb + j] = __float2bfloat16(v[j]);
+    }
+  }
+}
+
+template <int BN, int PSTAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                               int M, int N, int K, int taps, int pad, int a_batch_mul, int kb_per_split, int m_tiles,
+                               int n_tiles, int z_tiles, GemmEpilogue ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using L = GemmPSmem<BN, PSTAGES>;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + PSTAGES;
+  uint64_t* acc_full = empty_bar + PSTAGES;     // [2] MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;           // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kblocks_per_tap = K / BK;
+  const int kb_total = kblocks_per_tap * taps;
+  const int total_tiles = m_tiles * n_tiles * z_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < PSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile % m_tiles, rest = tile / m_tiles;
+        const int nt = rest % n_tiles, bz = rest / n_tiles;
+        const int m0 = mt * BM, n0 = nt * BN;
+        const int kb_begin = kb_per_split > 0 ? bz * kb_per_split : 0;
+        const int num_kb = kb_per_split > 0 ? min(kb_per_split, kb_total - kb_begin) : kb_total;
+        for (int kbi = 0; kbi < num_kb; ++kbi) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const int kb = kb_begin + kbi;
+          const int tap = kb / kblocks_per_tap;
+          const int kk = (kb - tap * kblocks_per_tap) * BK;
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          tma_load_3d(sa, &map_a, &full_bar[stage], kk, m0 + tap - pad, bz * a_batch_mul);
+          tma_load_3d(sb, &map_b, &full_bar[stage], tap * K + kk, n0, 0);
+          if (++stage == PSTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int t = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+        const int bz = tile / (m_tiles * n_tiles);
+        const int kb_begin = kb_per_split > 0 ? bz * kb_per_split : 0;
+        const int num_kb = kb_per_split > 0 ? min(kb_per_split, kb_total - kb_begin) : kb_total;
+        const int acc = t & 1;
+        mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_ss(tmem_d, umma_desc_kmajor_sw128(sa + k * 32), umma_desc_kmajor_sw128(sb + k * 32), idesc,
+                         (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == PSTAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int t = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      const int mt = tile % m_tiles, rest = tile / m_tiles;
+      const int nt = rest % n_tiles, bz = rest / n_tiles;
+      const int m = mt * BM + row, n0 = nt * BN;
+      const int acc = t & 1;
+      mbar_wait(&acc_full[acc], (t >> 1) & 1);
+      tc_fence_after();
+      const bool row_ok = m < M;
+      const float* res_row = ep.residual ? ep.residual + (long long)bz * ep.res_bstride + (long long)m * ep.ldr : nullptr;
+      float* of_row = ep.out_f32 ? ep.out_f32 + (long long)bz * ep.outf_bstride + (long long)m * ep.ldo : nullptr;
+      __nv_bfloat16* ob_row = ep.out_bf16 ? ep.out_bf16 + (long long)bz * ep.outb_bstride + (long long)m * ep.ldob : nullptr;
+      // pull the whole accumulator row into registers first, release the TMEM buffer, then do the memory-bound part
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), r);
+        tmem_ld_wait();
+        if (c + 32 >= BN) {          // last chunk read: the MMA warp may start overwriting this accumulator
+          tc_fence_before();
+          mbar_arrive(&acc_empty[acc]);
+        }
+        const int nb = n0 + c;
+        if (row_ok && nb < N) gemm_epilogue_chunk(r, nb, N, ep, res_row, of_row, ob_row);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<2 * BN>(tmem_base);
+  }
+}
+
+}  // namespace ttb
