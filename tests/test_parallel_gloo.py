@@ -53,3 +53,49 @@ def _worker(rank, ws, port, total, L):
 def test_gather_and_broadcast_world2():
     port = _free_port()
     mp.spawn(_worker, args=(2, port, 13, 9), nprocs=2, join=True)
+
+
+def test_render_plan():
+    assert parallel.render_plan(0, 1, True) == (0, None)
+    assert parallel.render_plan(3, 4, False) == (3, None)
+    assert [parallel.render_plan(j, 8, True) for j in range(5)] == [(0, 0), (2, 1), (4, 2), (6, 3), (0, 0)]
+    assert parallel.render_plan(0, 2, True) == (0, 0)
+
+
+def _pair_worker(rank, ws, port, ret):
+    """CFG branches split over a rank pair (one all-gather per step) == both branches on one rank."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import lib_emu
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        lib_emu.install()
+        from tortoise_tts_b200.config import ModelConfig
+        from tortoise_tts_b200.synth import synth_all
+        from tortoise_tts_b200.diffusion_engine import DiffusionEngine
+        cfg = ModelConfig.small()
+        sds = synth_all(cfg, seed=0, suppress_stop=False)
+        g = torch.Generator().manual_seed(5)
+        N, iters = 8, 3
+        S = N * 4 * 24000 // 22050
+        lat = torch.randn(N, cfg.ar_dim, generator=g)
+        cond = torch.randn(2 * cfg.diff_dim, generator=g) * 0.3
+        n0 = torch.randn(100, S, generator=g)
+        sn = torch.randn(iters, 100, S, generator=g)
+        groups, npairs = parallel.pair_groups()
+        assert npairs == 1
+        eng = DiffusionEngine(sds["diffusion"], cfg, device="cpu")
+        mel_pair = eng.sample(lat, cond, iters, n0, sn, cond_free=True, cond_free_k=2.0, use_graph=False,
+                              pair=(groups[0], rank))
+        eng2 = DiffusionEngine(sds["diffusion"], cfg, device="cpu")
+        mel_one = eng2.sample(lat, cond, iters, n0, sn, cond_free=True, cond_free_k=2.0, use_graph=False)
+        assert (mel_pair - mel_one).abs().max().item() < 1e-4
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cfg_pair_split_world2():
+    port = _free_port()
+    mp.spawn(_pair_worker, args=(2, port, None), nprocs=2, join=True)

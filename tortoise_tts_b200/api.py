@@ -166,7 +166,10 @@ class TextToSpeech:
             best = torch.topk(scores, k=k).indices
             best_codes = codes[best].contiguous()
             ev[2].record()
-            mine = [j for j in range(best_codes.shape[0]) if parallel.owner_of(j, ws) == rank]
+            # rendering plan: candidate j -> owner rank (+ the rank pair sharing its CFG denoiser when ws >= 2)
+            groups, _ = parallel.pair_groups() if (cond_free and ws >= 2) else (None, 0)
+            plan = [parallel.render_plan(j, ws, cond_free) for j in range(best_codes.shape[0])]
+            mine = [j for j, (owner, p) in enumerate(plan) if owner == rank or (p is not None and rank == owner + 1)]
             wavs = {}
             t_lat = t_diff = t_voc = 0.0
             timers = []
@@ -184,18 +187,21 @@ class TextToSpeech:
                 gj.manual_seed(seed + 7919 * (j + 1))
                 noise0 = torch.randn(100, S, generator=gj, device=dev) * diffusion_temperature
                 step_noise = torch.randn(diffusion_iterations, 100, S, generator=gj, device=dev)
+                owner, p = plan[j]
+                pair = None if p is None else (groups[p], rank - owner)
                 mel = self.diffusion.sample(lat, diff_cond, diffusion_iterations, noise0, step_noise, cond_free=cond_free,
-                                            cond_free_k=cond_free_k)
+                                            cond_free_k=cond_free_k, pair=pair)
                 e[2].record()
-                # the reference draws the vocoder noise on the CPU (vocoder.py:307); device draw here
-                z = torch.randn(64, S + 10, generator=gj, device=dev)
-                wavs[j] = self.vocoder.inference(mel, z)
+                if owner == rank:
+                    # the reference draws the vocoder noise on the CPU (vocoder.py:307); device draw here
+                    z = torch.randn(64, S + 10, generator=gj, device=dev)
+                    wavs[j] = self.vocoder.inference(mel, z)
                 e[3].record()
                 timers.append(e)
             ev[3].record()
             res = []
             for j in range(best_codes.shape[0]):
-                owner = parallel.owner_of(j, ws)
+                owner = plan[j][0]
                 if ws > 1:
                     n = torch.tensor([wavs[j].numel() if owner == rank else 0], dtype=torch.int64, device=dev)
                     torch.distributed.broadcast(n, src=owner)

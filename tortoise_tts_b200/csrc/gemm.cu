@@ -440,11 +440,15 @@ extern "C" int ttb_gemm(const TtbGemmArgs* gp, void* stream) {
   // tile choice: fill the 148 SMs; small-N / small-M problems use narrower tiles
   const long long tiles128 = (long long)((g.N + 127) / 128) * ((g.M + BM - 1) / BM) * g.batch;
   static int persist = -1;   // TTB_GEMM_PERSIST=0 selects the one-tile-per-CTA kernels (A/B comparison)
-  if (persist < 0) { const char* e = getenv("TTB_GEMM_PERSIST"); persist = (e && atoi(e) == 0) ? 0 : 1; }
-  if (persist && g.tile_n != 256) {
+  if (persist < 0) { const char* e = getenv("TTB_GEMM_PERSIST"); persist = e ? atoi(e) : 1; }
+  // Measured on B200 (profiles/op_profile_r01_*): the persistent kernel wins when there are several tiles per SM
+  // (CLVP: 131 -> 90 ms; diffusion qkv conv 66 -> 50 us) and loses on the skinny decode GEMMs (one wave of tiny tiles,
+  // where 2-4 resident CTAs per SM hide latency better than one deep pipeline), so it is used for >= 2 waves only.
+  if (persist && g.tile_n == 0 && tiles128 >= 2 * 148) return launch_persistent<128, 6>(g, ep, st);
+  if (persist == 2) {        // TTB_GEMM_PERSIST=2: force the persistent kernels everywhere (experiments)
     if (g.tile_n == 32) return launch_persistent<32, 8>(g, ep, st);
     if (g.tile_n == 64 || (g.tile_n == 0 && tiles128 < 148)) return launch_persistent<64, 8>(g, ep, st);
-    return launch_persistent<128, 6>(g, ep, st);
+    if (g.tile_n != 256) return launch_persistent<128, 6>(g, ep, st);
   }
   if (g.tile_n == 32) return launch_tc<32, 4>(g, ep, st);
   if (g.tile_n == 64 || (g.tile_n == 0 && tiles128 < 148)) return launch_tc<64, 4>(g, ep, st);

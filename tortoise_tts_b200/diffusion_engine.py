@@ -238,28 +238,40 @@ class DiffusionEngine:
         for j, rw in enumerate(self.tail):
             self._res_block(rw, st["ss_all"][n_int + len(self.layers) + j], x, B, S, ws, st["counter"])
         self._gn(x, B, S, self.out_g, self.out_b, ws, silu=True)
-        lib.gemm(ws["a"], self.w_outc, M=S, N=self.cout, K=C, taps=3, pad=1, bias=self.b_outc, out_f32=st["model_out"],
+        lib.gemm(ws["a"], self.w_outc, M=S, N=self.cout, K=C, taps=3, pad=1, bias=self.b_outc, out_f32=st["mo_local"],
                  batch=B, a_bstride=S * C, outf_bstride=S * self.cout)
 
     def _step(self, st):
         self._forward(st)
+        if st.get("pair") is not None:
+            # CFG pair split over 2 GPUs: this rank evaluated ONE branch (rank 0 of the pair = conditional, rank 1 =
+            # unconditional); one all-gather of the [S, 200] fp32 outputs (1.5 MB over NVLink) gives both ranks both
+            # branches, and both then run the identical scheduler epilogue (same pre-drawn noise) -> no second exchange.
+            import torch.distributed as dist
+            if st["model_out"].is_cuda:
+                dist.all_gather_into_tensor(st["model_out"].view(-1), st["mo_local"].view(-1), group=st["pair"][0])
+            else:   # gloo (CPU tests of the host logic)
+                dist.all_gather([st["model_out"][0], st["model_out"][1]], st["mo_local"][0], group=st["pair"][0])
         lib.diffusion_step(st["model_out"], st["S"] * self.cout, self.cout, st["x"], st["x_bf"], self.cin_pad, st["noise"],
                            st["tables"], st["counter"], st["S"], self.cin, st["iters"], st["cond_free"],
                            st["cond_free_k"], st["mel"])
         lib.counter_add(st["counter"], 1)
 
-    def _state(self, S, B, iters, cfk=0.0):
-        key = (S, B, iters, cfk)
+    def _state(self, S, B, iters, cfk=0.0, pair=None):
+        """B = number of CFG branches evaluated ON THIS RANK (2, or 1 when the pair is split over two GPUs / no CFG)."""
+        key = (S, B, iters, cfk, None if pair is None else pair[1])
         if self._ws is not None and self._ws["key"] == key:
+            self._ws["pair"] = pair
             return self._ws
         C, dev = self.C, self.dev
-        st = dict(key=key, S=S, B=B, iters=iters)
+        st = dict(key=key, S=S, B=B, iters=iters, pair=pair)
         st["ws"] = self._alloc(B, S)
         st["xce"] = torch.empty(B, S, C, dtype=torch.float32, device=dev)
         st["code_emb_init"] = torch.empty(B, S, C, dtype=torch.float32, device=dev)
         st["cat"] = torch.empty(B, S, 2 * C, dtype=torch.bfloat16, device=dev)
         st["xm"] = torch.empty(B, S, C, dtype=torch.float32, device=dev)
-        st["model_out"] = torch.empty(B, S, self.cout, dtype=torch.float32, device=dev)
+        st["model_out"] = torch.empty(2 if pair is not None else B, S, self.cout, dtype=torch.float32, device=dev)
+        st["mo_local"] = torch.empty(1, S, self.cout, dtype=torch.float32, device=dev) if pair is not None else st["model_out"]
         st["x"] = torch.empty(S, self.cin, dtype=torch.float32, device=dev)
         st["x_bf"] = torch.zeros(S, self.cin_pad, dtype=torch.bfloat16, device=dev)
         st["noise"] = torch.empty(iters, S, self.cin, dtype=torch.float32, device=dev)
@@ -305,20 +317,26 @@ class DiffusionEngine:
         return mo[0].t().contiguous(), mo[1].t().contiguous()
 
     def sample(self, latents, cond_latent, iters, noise0, step_noise, cond_free=True, cond_free_k=2.0, use_graph=True,
-               return_trace=False):
+               return_trace=False, pair=None):
         """≙ do_spectrogram_diffusion (api.py:117-130). latents [N, ar_dim], cond_latent [2C];
         noise0 [100, S] (already scaled by the temperature), step_noise [iters, 100, S] in call order.
         Returns the denormalised mel fp32 [100, S] (channel-major, as the reference returns it)."""
         C, dev = self.C, self.dev
         N = latents.shape[0]
         S = N * 4 * 24000 // 22050
-        B = 2 if cond_free else 1
+        # pair = (process group of 2 ranks, my rank in it): the two CFG branches run on two GPUs (see _step)
+        if not cond_free:
+            pair = None
+        B = 1 if (pair is not None or not cond_free) else 2
         tmap, tables = make_schedule(iters)
         n = len(tmap)
-        st = self._state(S, B, n, float(cond_free_k))
+        st = self._state(S, B, n, float(cond_free_k), pair)
         st["cond_free"], st["cond_free_k"] = bool(cond_free), float(cond_free_k)
-        code_emb = self.timestep_independent(latents, cond_latent, S)
-        st["code_emb_init"][0].copy_(code_emb)
+        if pair is None or pair[1] == 0:
+            code_emb = self.timestep_independent(latents, cond_latent, S)
+            st["code_emb_init"][0].copy_(code_emb)
+        else:
+            lib.broadcast_rows(self.uncond, S, C, st["code_emb_init"][0], None, C)
         if B == 2:
             lib.broadcast_rows(self.uncond, S, C, st["code_emb_init"][1], None, C)
         st["tables"].copy_(torch.from_numpy(tables))

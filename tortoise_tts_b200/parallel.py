@@ -28,6 +28,31 @@ def owner_of(j, world_size):
     return j % world_size
 
 
+_PAIR_GROUPS = None
+
+
+def pair_groups():
+    """Process groups of rank pairs (2p, 2p+1) used to split the two classifier-free-guidance branches of the denoiser
+    over two GPUs. Created collectively (every rank calls new_group for every pair, in the same order) on first use.
+    Returns (groups list, number of pairs) or (None, 0) when the world has fewer than 2 ranks."""
+    global _PAIR_GROUPS
+    rank, ws = world()
+    if ws < 2:
+        return None, 0
+    if _PAIR_GROUPS is None:
+        _PAIR_GROUPS = [dist.new_group([2 * p, 2 * p + 1]) for p in range(ws // 2)]
+    return _PAIR_GROUPS, ws // 2
+
+
+def render_plan(j, world_size, cond_free):
+    """Who renders (diffusion + vocoder) the j-th selected candidate: returns (owner rank, pair index or None).
+    With CFG and >= 2 ranks, pair p = j % (G//2) = ranks (2p, 2p+1) share the denoiser; rank 2p owns the waveform."""
+    if cond_free and world_size >= 2:
+        p = j % (world_size // 2)
+        return 2 * p, p
+    return owner_of(j, world_size), None
+
+
 def gather_candidates(scores, codes, total):
     """All-gather of per-rank CLVP scores [b] and codes [b, L] -> ([total], [total, L]) in global candidate order.
     One fused collective: scores are bit-cast into an extra int32 column of the codes buffer."""
