@@ -167,8 +167,9 @@ class TextToSpeech:
             best_codes = codes[best].contiguous()
             ev[2].record()
             # rendering plan: candidate j -> owner rank (+ the rank pair sharing its CFG denoiser when ws >= 2)
-            groups, _ = parallel.pair_groups() if (cond_free and ws >= 2) else (None, 0)
-            plan = [parallel.render_plan(j, ws, cond_free) for j in range(best_codes.shape[0])]
+            use_pair = cond_free and ws >= 2 and os.environ.get("TTB_CFG_PAIR", "0") == "1"   # opt-in
+            groups, _ = parallel.pair_groups() if use_pair else (None, 0)
+            plan = [parallel.render_plan(j, ws, use_pair) for j in range(best_codes.shape[0])]
             mine = [j for j, (owner, p) in enumerate(plan) if owner == rank or (p is not None and rank == owner + 1)]
             wavs = {}
             t_lat = t_diff = t_voc = 0.0

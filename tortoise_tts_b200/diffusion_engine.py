@@ -353,6 +353,10 @@ class DiffusionEngine:
 
         def one():
             self._step(st)
+        # torch.distributed NCCL collectives are not captured into the CUDA graph (a capture attempt dead-locked on the
+        # GPU box in round 1): the pair-split path runs eagerly (GPU-bound at B=1: ~125 launches per 2.5 ms step)
+        if pair is not None:
+            use_graph = False
         if use_graph and not return_trace:
             if st["graph"] is None:
                 one()  # eager warm-up (counter -> 1), then rewind
