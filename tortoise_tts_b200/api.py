@@ -167,7 +167,7 @@ class TextToSpeech:
             best_codes = codes[best].contiguous()
             ev[2].record()
             # rendering plan: candidate j -> owner rank (+ the rank pair sharing its CFG denoiser when ws >= 2)
-            use_pair = cond_free and ws >= 2 and os.environ.get("TTB_CFG_PAIR", "0") == "1"   # opt-in
+            use_pair = cond_free and ws >= 2 and os.environ.get("TTB_CFG_PAIR", "1") == "1"   # TTB_CFG_PAIR=0 disables
             groups, _ = parallel.pair_groups() if use_pair else (None, 0)
             plan = [parallel.render_plan(j, ws, use_pair) for j in range(best_codes.shape[0])]
             mine = [j for j, (owner, p) in enumerate(plan) if owner == rank or (p is not None and rank == owner + 1)]

@@ -243,6 +243,9 @@ class DiffusionEngine:
 
     def _step(self, st):
         self._forward(st)
+        self._epilogue(st)
+
+    def _epilogue(self, st):
         if st.get("pair") is not None:
             # CFG pair split over 2 GPUs: this rank evaluated ONE branch (rank 0 of the pair = conditional, rank 1 =
             # unconditional); one all-gather of the [S, 200] fp32 outputs (1.5 MB over NVLink) gives both ranks both
@@ -351,38 +354,48 @@ class DiffusionEngine:
         st["counter"].zero_()
         trace = []
 
-        def one():
-            self._step(st)
-        # torch.distributed NCCL collectives are not captured into the CUDA graph (a capture attempt dead-locked on the
-        # GPU box in round 1): the pair-split path runs eagerly (GPU-bound at B=1: ~125 launches per 2.5 ms step)
-        if pair is not None:
-            use_graph = False
+        # The CUDA graph holds the denoiser evaluation (+ the scheduler epilogue when both CFG branches are local).
+        # In pair mode the NCCL all-gather is NOT captured (a capture attempt of torch.distributed collectives dead-locked
+        # on the GPU box in round 1): graph(forward of my branch) -> eager all-gather -> eager epilogue, per step.
+        def captured():
+            if pair is None:
+                self._step(st)
+            else:
+                self._forward(st)
+
+        def after():
+            if pair is not None:
+                self._epilogue(st)
+
+        def rewind():
+            st["counter"].zero_()
+            lib.transpose_f32(_f(noise0.reshape(self.cin, S), dev), self.cin, S, st["x"])
+            lib.cast_pad_bf16(st["x"], S, self.cin, self.cin, st["x_bf"], self.cin_pad)
         if use_graph and not return_trace:
             if st["graph"] is None:
-                one()  # eager warm-up (counter -> 1), then rewind
+                captured()  # eager warm-up, then rewind
+                after()
                 torch.cuda.synchronize()
-                st["counter"].zero_()
-                lib.transpose_f32(_f(noise0.reshape(self.cin, S), dev), self.cin, S, st["x"])
-                lib.cast_pad_bf16(st["x"], S, self.cin, self.cin, st["x_bf"], self.cin_pad)
+                rewind()
                 g = torch.cuda.CUDAGraph()
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
                 c0 = lib.CALLS
                 with torch.cuda.stream(side):
                     with torch.cuda.graph(g, stream=side):
-                        one()
+                        captured()
                 st["graph_calls"] = lib.CALLS - c0
                 torch.cuda.current_stream().wait_stream(side)
                 st["graph"] = g
-                st["counter"].zero_()
-                lib.transpose_f32(_f(noise0.reshape(self.cin, S), dev), self.cin, S, st["x"])
-                lib.cast_pad_bf16(st["x"], S, self.cin, self.cin, st["x_bf"], self.cin_pad)
+                rewind()
             for _ in range(n):
                 st["graph"].replay()
+                after()
             lib.add_calls(n * st["graph_calls"])
         else:
             for _ in range(n):
-                one()
+                captured()
+                after()
                 if return_trace:
                     trace.append(st["x"].t().contiguous().clone())
         mel = st["mel"].clone()
