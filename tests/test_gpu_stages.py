@@ -66,6 +66,68 @@ def test_ar_logits_full_width(medium):
     assert r < 0.03
 
 
+def test_full_depth_parity():
+    """FULL-size models (30-layer GPT-2, 20-layer CLVP encoders, 10+3+3-layer denoiser) on short inputs against the CPU
+    oracle: the error bf16 operands accumulate through the real depth."""
+    from tortoise_tts_b200.config import ModelConfig
+    from tortoise_tts_b200 import synth
+    from tortoise_tts_b200.ar_engine import AREngine
+    from tortoise_tts_b200.clvp_engine import CLVPEngine
+    from tortoise_tts_b200.diffusion_engine import DiffusionEngine
+    from oracle import ar, clvp, diffusion as od
+    cfg = ModelConfig.full()
+    torch.manual_seed(0)
+    text = torch.randint(1, 255, (20,)).tolist() + [0]
+    # ---- AR: teacher-forced logits + decode loop logits
+    sd = synth.synth_autoregressive(cfg, seed=3, suppress_stop=False)
+    cond = torch.randn(1, cfg.ar_dim) * 0.5
+    codes = torch.randint(0, 8192, (2, 6))
+    with torch.no_grad():
+        want = ar.teacher_forced_logits(sd, cfg, cond, text, codes)
+    eng = AREngine(sd, cfg)
+    r = _rel(eng.teacher_forced_logits(cond, text, codes).cpu(), want)
+    report("FULL ar_logits (30 layers)", r)
+    assert r < 0.05
+    tr = []
+    u = torch.rand(2, 6)
+    c = eng.generate(cond, text, 2, 6, uniforms=u, trace_logits=tr).cpu().long()
+    with torch.no_grad():
+        want = ar.teacher_forced_logits(sd, cfg, cond, text, c[:, :-1])
+    r = _rel(torch.stack([t.cpu() for t in tr], dim=1), want)
+    report("FULL ar decode-loop logits (30 layers)", r)
+    assert r < 0.05
+    del eng, sd
+    torch.cuda.empty_cache()
+    # ---- CLVP
+    sd = synth.synth_clvp(cfg, seed=3)
+    ccodes = torch.randint(0, 8192, (3, 40))
+    with torch.no_grad():
+        want = clvp.scores(sd, cfg, torch.tensor(text), ccodes)
+    got = CLVPEngine(sd, cfg).scores(text, ccodes).cpu()
+    err = (got - want).abs().max().item()
+    report("FULL clvp scores abs (20 layers)", err)
+    assert err < 0.05
+    del sd
+    # ---- denoiser forward
+    sd = synth.synth_diffusion(cfg, seed=3)
+    N = 30
+    S = N * 4 * 24000 // 22050
+    lat = torch.randn(N, cfg.ar_dim)
+    dcond = torch.randn(2 * cfg.diff_dim) * 0.3
+    x = torch.randn(1, 100, S)
+    deng = DiffusionEngine(sd, cfg)
+    ce_g = deng.timestep_independent(lat, dcond, S)
+    with torch.no_grad():
+        ce = od.timestep_independent(sd, cfg, lat.unsqueeze(0), dcond.unsqueeze(0), S)
+        got_c, got_u = deng.forward_once(x[0], 2000, ce_g)
+        want_c = od.forward(sd, cfg, x, torch.tensor([2000]), code_emb=ce)
+        want_u = od.forward(sd, cfg, x, torch.tensor([2000]), conditioning_free=True)
+    rc, ru = _rel(got_c.cpu(), want_c[0]), _rel(got_u.cpu(), want_u[0])
+    report("FULL diffusion forward cond (16 layers)", rc)
+    report("FULL diffusion forward uncond (16 layers)", ru)
+    assert rc < 0.05 and ru < 0.05
+
+
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_ar_generate_decode_path(small, use_graph):
     """The KV-cached decode loop (prefill + shared-prefix decode attention + fused sampler, optionally as a CUDA
