@@ -45,6 +45,8 @@ typedef struct TtbGemmArgs {
   int force_ref;        /* 1 = SIMT checker kernel (tests only) */
   int splitk;           /* > 1: split the reduction over grid.z; writes raw fp32 partials out_f32[split][M][ldo]
                            (outf_bstride = stride between splits); batch must be 1, no epilogue fusion */
+  int cluster;          /* 2 or 4: CTAs adjacent in N form a cluster and share the activation tile by TMA multicast
+                           (tile_n picks the tile width: 32, 64, else 128); 0/1 = off */
 } TtbGemmArgs;
 
 /* nn.Linear / HF Conv1D / nn.Conv1d(k=1,3) as one tcgen05 GEMM with fused bias/activation/residual.

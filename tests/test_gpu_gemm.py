@@ -121,6 +121,42 @@ def test_gemm_skinny_splitk(M, N, K, tile_n, splitk):
     assert err < 2e-3
 
 
+@pytest.mark.parametrize("M,N,K,tile_n,cluster,splitk,taps,batch", [
+    (256, 3072, 1024, 32, 4, 1, 1, 1), (256, 1024, 4096, 32, 4, 4, 1, 1), (256, 4096, 1024, 64, 2, 1, 1, 1),
+    (1872, 1024, 1024, 128, 4, 1, 3, 2), (300, 512, 128, 128, 2, 1, 1, 1), (77, 256, 256, 64, 4, 1, 3, 2)])
+def test_gemm_cluster_multicast(M, N, K, tile_n, cluster, splitk, taps, batch):
+    """Thread-block clusters along N with the activation tile multicast by TMA (gemm_mc.cuh)."""
+    from tortoise_tts_b200 import lib
+    A = _mk((batch, M, K), 1.0, 15).to(torch.bfloat16)
+    W = _mk((N, taps, K), (K * taps) ** -0.5, 16).to(torch.bfloat16)
+    a, w = A.float().cpu(), W.float().cpu()
+    want = torch.zeros(batch, M, N)
+    pad = (taps - 1) // 2
+    for tap in range(taps):
+        sh = tap - pad
+        lo, hi = max(0, -sh), min(M, M - sh)
+        want[:, lo:hi] += a[:, lo + sh:hi + sh] @ w[:, tap].t()
+    want = want.cuda()
+    if splitk == 1:
+        b = _mk((N,), 0.5, 17)
+        out = torch.full((batch, M, N), float("nan"), device="cuda")
+        lib.gemm(A, W.reshape(N, taps * K), M=M, N=N, K=K, taps=taps, pad=pad, batch=batch, bias=b, out_f32=out,
+                 a_bstride=M * K, outf_bstride=M * N, tile_n=tile_n, cluster=cluster)
+        got = out - b
+    else:
+        kb = K // 64
+        per = (kb + splitk - 1) // splitk
+        nz = (kb + per - 1) // per
+        part = torch.full((nz, M, N), float("nan"), device="cuda")
+        lib.gemm(A, W.reshape(N, K), M=M, N=N, K=K, out_f32=part, outf_bstride=M * N, tile_n=tile_n, splitk=splitk,
+                 cluster=cluster)
+        got = part.sum(dim=0).unsqueeze(0)
+    torch.cuda.synchronize()
+    err = (got - want).abs().max().item() / want.abs().max().item()
+    report("gemm cluster M=%d N=%d K=%d tile=%d cl=%d splitk=%d taps=%d" % (M, N, K, tile_n, cluster, splitk, taps), err)
+    assert err < 2e-3
+
+
 @pytest.mark.parametrize("case", [CASES[3], CASES[8], CASES[10]], ids=["tails", "conv3", "geglu"])
 def test_gemm_simt_checker(case):
     y, of, ob = _run(force_ref=True, **case)

@@ -357,6 +357,7 @@ static int launch_tc(const TtbGemmArgs& g, const GemmEpilogue& ep, cudaStream_t 
 }  // namespace ttb
 
 #include "gemm_persist.cuh"
+#include "gemm_mc.cuh"
 
 namespace ttb {
 
@@ -439,6 +440,18 @@ extern "C" int ttb_gemm(const TtbGemmArgs* gp, void* stream) {
   }
   // tile choice: fill the 148 SMs; small-N / small-M problems use narrower tiles
   const long long tiles128 = (long long)((g.N + 127) / 128) * ((g.M + BM - 1) / BM) * g.batch;
+  if (g.cluster > 1) {
+    // thread-block clusters along N sharing the activation tile by TMA multicast (gemm_mc.cuh)
+    const int bn = g.tile_n == 32 ? 32 : (g.tile_n == 64 ? 64 : 128);
+    const int n_tiles = (g.N + bn - 1) / bn;
+    if ((g.cluster != 2 && g.cluster != 4) || n_tiles % g.cluster != 0) {
+      set_error("ttb_gemm: cluster=%d needs 2 or 4 and a multiple of it in N tiles (%d)", g.cluster, n_tiles);
+      return -1;
+    }
+    if (bn == 32) return g.cluster == 4 ? launch_mc<32, 4, 4>(g, ep, st) : launch_mc<32, 4, 2>(g, ep, st);
+    if (bn == 64) return g.cluster == 4 ? launch_mc<64, 4, 4>(g, ep, st) : launch_mc<64, 4, 2>(g, ep, st);
+    return g.cluster == 4 ? launch_mc<128, 3, 4>(g, ep, st) : launch_mc<128, 3, 2>(g, ep, st);
+  }
   static int persist = -1;   // TTB_GEMM_PERSIST=0 selects the one-tile-per-CTA kernels (A/B comparison)
   if (persist < 0) { const char* e = getenv("TTB_GEMM_PERSIST"); persist = e ? atoi(e) : 1; }
   // Measured on B200 (profiles/op_profile_r01_*): the persistent kernel wins when there are several tiles per SM

@@ -158,6 +158,10 @@ class DiffusionEngine:
         self.b_outc = _f(sd["out.2.bias"], dev)
         self.res_all = [r for r, _ in self.integ] + [r for r, _ in self.layers] + self.tail
         self._ws = None
+        # TMA-multicast clusters along N for the C x C convs (TTB_DIFF_CLUSTER=0 disables); needs C/128 tiles % CL == 0
+        import os
+        cl = int(os.environ.get("TTB_DIFF_CLUSTER", "0"))
+        self.CL = cl if (cl in (2, 4) and (C // 128) % cl == 0) else 0
 
     # ------------------------------------------------------------------ building blocks on [B, S, C] fp32 (in place)
     def _gn(self, x, B, S, g, b, ws, silu=False, ss=None, ss_row=None, out=None):
@@ -168,21 +172,21 @@ class DiffusionEngine:
         C, H = self.C, self.H
         self._gn(x, B, S, aw.gn_g, aw.gn_b, ws)
         lib.gemm(ws["a"], aw.wqkv, M=S, N=3 * C, K=C, bias=aw.bqkv, out_bf16=ws["qkv"], batch=B, a_bstride=S * C,
-                 outb_bstride=S * 3 * C)
+                 outb_bstride=S * 3 * C, cluster=self.CL)
         # T5 buckets saturate at max_distance = 64 (xtransformers.py:166-174): |j - i| >= 64 -> constant bias per side
         lib.attention(ws["qkv"], ws["o"], nseq=B, T=S, H=H, ld=3 * C, ldo=C, k_off=C, v_off=2 * C, scale=0.125,
                       bias=aw.table(S), bias_sat=64)
         lib.gemm(ws["o"], aw.wproj, M=S, N=C, K=C, bias=aw.bproj, residual=x, out_f32=x, batch=B, a_bstride=S * C,
-                 res_bstride=S * C, outf_bstride=S * C)
+                 res_bstride=S * C, outf_bstride=S * C, cluster=self.CL)
 
     def _res_block(self, rw, ss, x, B, S, ws, ss_row=None):
         C = self.C
         self._gn(x, B, S, rw.in_g, rw.in_b, ws, silu=True)
         lib.gemm(ws["a"], rw.w_in, M=S, N=C, K=C, bias=rw.b_in, out_f32=ws["h"], batch=B, a_bstride=S * C,
-                 outf_bstride=S * C)
+                 outf_bstride=S * C, cluster=self.CL)
         self._gn(ws["h"], B, S, rw.out_g, rw.out_b, ws, silu=True, ss=ss, ss_row=ss_row)
         lib.gemm(ws["a"], rw.w_out, M=S, N=C, K=C, taps=3, pad=1, bias=rw.b_out, residual=x, out_f32=x, batch=B,
-                 a_bstride=S * C, res_bstride=S * C, outf_bstride=S * C)
+                 a_bstride=S * C, res_bstride=S * C, outf_bstride=S * C, cluster=self.CL)
 
     def _alloc(self, B, S):
         C, dev = self.C, self.dev
