@@ -103,6 +103,10 @@ struct GemmEpilogue {
   float alpha;             // scales the accumulator before bias
 };
 
+}  // namespace ttb
+#include "gemm_epilogue.cuh"
+namespace ttb {
+
 template <int BN, int STAGES>
 struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
@@ -197,12 +201,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const float* res_row = ep.residual ? ep.residual + (long long)bz * ep.res_bstride + (long long)m * ep.ldr : nullptr;
     float* of_row = ep.out_f32 ? ep.out_f32 + (long long)bz * ep.outf_bstride + (long long)m * ep.ldo : nullptr;
     __nv_bfloat16* ob_row = ep.out_bf16 ? ep.out_bf16 + (long long)bz * ep.outb_bstride + (long long)m * ep.ldob : nullptr;
+    // all MMAs have retired: the pipeline stages are idle and serve as the per-warp transpose scratch
+    float* scratch = reinterpret_cast<float*>(smem + (warp - 2) * EPI_SCRATCH_BYTES);
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       uint32_t r[32];
       tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
       tmem_ld_wait();
       const int nb = n0 + c;
+      gemm_epilogue_coalesced(r, nb, N, m0 + q * 32, M, lane, (long long)bz, ep, scratch);
+      continue;   // (the per-row store path below is kept for reference only; see gemm_epilogue.cuh)
       if (!row_ok || nb >= N) continue;
       float v[32];
 #pragma unroll

@@ -123,13 +123,14 @@ gemm_bf16_tc_mc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     const float* res_row = ep.residual ? ep.residual + (long long)bz * ep.res_bstride + (long long)m * ep.ldr : nullptr;
     float* of_row = ep.out_f32 ? ep.out_f32 + (long long)bz * ep.outf_bstride + (long long)m * ep.ldo : nullptr;
     __nv_bfloat16* ob_row = ep.out_bf16 ? ep.out_bf16 + (long long)bz * ep.outb_bstride + (long long)m * ep.ldob : nullptr;
+    float* scratch = reinterpret_cast<float*>(smem + (warp - 2) * EPI_SCRATCH_BYTES);   // stages are idle by now
+    (void)row_ok; (void)res_row; (void)of_row; (void)ob_row;
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       uint32_t r[32];
       tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
       tmem_ld_wait();
-      const int nb = n0 + c;
-      if (row_ok && nb < N) gemm_epilogue_chunk(r, nb, N, ep, res_row, of_row, ob_row);
+      gemm_epilogue_coalesced(r, n0 + c, N, m0 + q * 32, M, lane, (long long)bz, ep, scratch);
     }
     tc_fence_before();
   }

@@ -15,7 +15,8 @@ struct GemmPSmem {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = PSTAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + (2 * PSTAGES + 4) * 8 + 16 + 1024;
+  static constexpr int SCRATCH_OFF = BAR_OFF + (2 * PSTAGES + 4) * 8 + 16;   // 4 epilogue warps x [32][33] floats
+  static constexpr int TOTAL = SCRATCH_OFF + 4 * EPI_SCRATCH_BYTES + 1024;
 };
 
 // epilogue of one 32-column chunk held in registers (thread = one output row)
@@ -201,9 +202,10 @@ gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const 
           tc_fence_before();
           mbar_arrive(&acc_empty[acc]);
         }
-        const int nb = n0 + c;
-        if (row_ok && nb < N) gemm_epilogue_chunk(r, nb, N, ep, res_row, of_row, ob_row);
+        gemm_epilogue_coalesced(r, n0 + c, N, mt * BM + q * 32, M, lane, (long long)bz, ep,
+                                reinterpret_cast<float*>(smem + L::SCRATCH_OFF + (warp - 2) * EPI_SCRATCH_BYTES));
       }
+      (void)row_ok; (void)res_row; (void)of_row; (void)ob_row;
     }
   }
   __syncthreads();
