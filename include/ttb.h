@@ -47,6 +47,7 @@ typedef struct TtbGemmArgs {
                            (outf_bstride = stride between splits); batch must be 1, no epilogue fusion */
   int cluster;          /* 2 or 4: CTAs adjacent in N form a cluster and share the activation tile by TMA multicast
                            (tile_n picks the tile width: 32, 64, else 128); 0/1 = off */
+  int variant;          /* 0 = auto; 1 = one tile per CTA; 2 = persistent kernel (tools/gemm_sweep.py) */
 } TtbGemmArgs;
 
 /* nn.Linear / HF Conv1D / nn.Conv1d(k=1,3) as one tcgen05 GEMM with fused bias/activation/residual.

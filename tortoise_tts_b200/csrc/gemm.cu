@@ -465,8 +465,14 @@ extern "C" int ttb_gemm(const TtbGemmArgs* gp, void* stream) {
   // Measured on B200 (profiles/op_profile_r01_*): the persistent kernel wins when there are several tiles per SM
   // (CLVP: 131 -> 90 ms; diffusion qkv conv 66 -> 50 us) and loses on the skinny decode GEMMs (one wave of tiny tiles,
   // where 2-4 resident CTAs per SM hide latency better than one deep pipeline), so it is used for >= 2 waves only.
-  if (persist && g.tile_n == 0 && tiles128 >= 2 * 148) return launch_persistent<128, 6>(g, ep, st);
-  if (persist == 2) {        // TTB_GEMM_PERSIST=2: force the persistent kernels everywhere (experiments)
+  if (g.variant == 2) {
+    if (g.tile_n == 32) return launch_persistent<32, 8>(g, ep, st);
+    if (g.tile_n == 64) return launch_persistent<64, 8>(g, ep, st);
+    return launch_persistent<128, 6>(g, ep, st);
+  }
+  const int use_persist = (g.variant == 1) ? 0 : persist;
+  if (use_persist && g.tile_n == 0 && tiles128 >= 2 * 148) return launch_persistent<128, 6>(g, ep, st);
+  if (use_persist == 2) {        // TTB_GEMM_PERSIST=2: force the persistent kernels everywhere (experiments)
     if (g.tile_n == 32) return launch_persistent<32, 8>(g, ep, st);
     if (g.tile_n == 64 || (g.tile_n == 0 && tiles128 < 148)) return launch_persistent<64, 8>(g, ep, st);
     if (g.tile_n != 256) return launch_persistent<128, 6>(g, ep, st);

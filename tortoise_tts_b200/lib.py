@@ -25,7 +25,7 @@ class GemmArgs(C.Structure):
                 ("lda", C.c_int), ("ldr", C.c_int), ("ldo", C.c_int), ("ldob", C.c_int),
                 ("rows", C.c_int), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
                 ("taps", C.c_int), ("pad", C.c_int), ("batch", C.c_int), ("act", C.c_int),
-                ("alpha", C.c_float), ("tile_n", C.c_int), ("force_ref", C.c_int), ("splitk", C.c_int), ("cluster", C.c_int)]
+                ("alpha", C.c_float), ("tile_n", C.c_int), ("force_ref", C.c_int), ("splitk", C.c_int), ("cluster", C.c_int), ("variant", C.c_int)]
 
 
 class AttnArgs(C.Structure):
@@ -110,7 +110,7 @@ def _f32(t):
 # ------------------------------------------------------------------ wrappers
 def gemm(A, W, *, M, N, K, bias=None, residual=None, out_f32=None, out_bf16=None, lda=None, rows=None, batch=1,
          a_bstride=0, res_bstride=0, outf_bstride=0, outb_bstride=0, ldr=None, ldo=None, ldob=None, taps=1, pad=0,
-         act=ACT_NONE, alpha=1.0, tile_n=0, force_ref=False, splitk=1, cluster=0):
+         act=ACT_NONE, alpha=1.0, tile_n=0, force_ref=False, splitk=1, cluster=0, variant=0):
     """See include/ttb.h ttb_gemm. A: bf16 [batch, rows, lda]; W: bf16 [N, taps*K]."""
     _bf(A), _bf(W), _f32(bias), _f32(residual), _f32(out_f32), _bf(out_bf16)
     n_out = N // 2 if act == ACT_GEGLU else N
@@ -125,6 +125,7 @@ def gemm(A, W, *, M, N, K, bias=None, residual=None, out_f32=None, out_bf16=None
     g.rows = M if rows is None else rows
     g.M, g.N, g.K, g.taps, g.pad, g.batch, g.act = M, N, K, taps, pad, batch, act
     g.alpha, g.tile_n, g.force_ref, g.splitk, g.cluster = alpha, tile_n, 1 if force_ref else 0, splitk, cluster
+    g.variant = variant
     _chk(load().ttb_gemm(C.byref(g), _stream()), "ttb_gemm")
 
 
