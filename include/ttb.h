@@ -57,6 +57,11 @@ typedef struct TtbGemmArgs {
  * KernelPredictor.kernel_conv (models/vocoder.py:59-62). */
 int ttb_gemm(const TtbGemmArgs* args, void* stream);
 
+/* Development aid (no reference counterpart): when buf != NULL every one-tile-per-CTA ttb_gemm launch writes 8 x u64
+ * per CTA into it (globaltimer ns at: start, [1]=SM id, setup done, first operands landed, last MMA issued,
+ * accumulator complete, epilogue done, exit). The buffer must hold 8 * grid-size u64. NULL switches tracing off. */
+int ttb_debug_gemm_trace(void* buf);
+
 /* ---------------------------------------------------------------- normalisation */
 /* y = LN(x) (eps 1e-5), optionally followed by a second LN (gpt.ln_f then final_norm,
  * autoregressive.py:42,174,348). x fp32 [M, D]; writes bf16 and/or fp32. */

@@ -74,6 +74,17 @@ TTB_DEVINL float2 unpack_bf16(uint32_t u) {
 
 TTB_DEVINL uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+TTB_DEVINL unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+TTB_DEVINL unsigned long long sm_id() {
+  uint32_t s;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(s));
+  return s;
+}
+
 TTB_DEVINL bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

@@ -117,12 +117,16 @@ struct GemmSmem {
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS)
+__global__ void __launch_bounds__(GEMM_THREADS, BN <= 128 ? 2 : 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
-                    int K, int taps, int pad, int a_batch_mul, int kb_per_split, GemmEpilogue ep) {
+                    int K, int taps, int pad, int a_batch_mul, int kb_per_split, GemmEpilogue ep,
+                    unsigned long long* trace) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using L = GemmSmem<BN, STAGES>;
+  // optional per-CTA phase timestamps (ttb_debug_gemm_trace): 8 x u64 per CTA, see tools/gemm_diag.py
+  unsigned long long* tr = trace ? trace + 8ull * (blockIdx.x + gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z)) : nullptr;
+  if (tr && threadIdx.x == 0) { tr[0] = global_timer_ns(); tr[1] = sm_id(); }
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* accum_bar = empty_bar + STAGES;
@@ -151,6 +155,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tr && threadIdx.x == 0) tr[2] = global_timer_ns();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -177,6 +182,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        if (tr && kb == 0) tr[3] = global_timer_ns();
         const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
         const uint32_t sb = sa + L::A_BYTES;
 #pragma unroll
@@ -189,107 +195,36 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       umma_commit(accum_bar);
+      if (tr) tr[4] = global_timer_ns();
     }
   } else {
     // ===== epilogue: warps 2..5; warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
     const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int m = m0 + row;
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const bool row_ok = m < M;
-    const float* res_row = ep.residual ? ep.residual + (long long)bz * ep.res_bstride + (long long)m * ep.ldr : nullptr;
-    float* of_row = ep.out_f32 ? ep.out_f32 + (long long)bz * ep.outf_bstride + (long long)m * ep.ldo : nullptr;
-    __nv_bfloat16* ob_row = ep.out_bf16 ? ep.out_bf16 + (long long)bz * ep.outb_bstride + (long long)m * ep.ldob : nullptr;
-    // all MMAs have retired: the pipeline stages are idle and serve as the per-warp transpose scratch
-    float* scratch = reinterpret_cast<float*>(smem + (warp - 2) * EPI_SCRATCH_BYTES);
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-      tmem_ld_wait();
-      const int nb = n0 + c;
-      gemm_epilogue_coalesced(r, nb, N, m0 + q * 32, M, lane, (long long)bz, ep, scratch);
-      continue;   // (the per-row store path below is kept for reference only; see gemm_epilogue.cuh)
-      if (!row_ok || nb >= N) continue;
-      float v[32];
+    if (ep.residual) {
+      // these warps idle during the mainloop: pull the tile's residual rows into L2 meanwhile
+      const int m = m0 + q * 32 + lane;
+      if (m < M) {
+        const float* p = ep.residual + (long long)bz * ep.res_bstride + (long long)m * ep.ldr + n0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(r[j]) * ep.alpha;
-        if (ep.bias && nb + j < N) x += __ldg(ep.bias + nb + j);
-        v[j] = x;
-      }
-      if (ep.act == TTB_ACT_GEGLU) {
-        // columns interleaved (u0,g0,u1,g1,...): out[j] = u * gelu_erf(g); output width N/2
-        float o[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf(v[2 * j + 1]);
-        const int ob = nb >> 1;
-        if (ob_row) {
-          if (nb + 32 <= N) {
-            uint4* dst = reinterpret_cast<uint4*>(ob_row + ob);
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-              dst[j] = make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
-                                  pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
-          } else {
-            for (int j = 0; j < 16 && nb + 2 * j < N; ++j) ob_row[ob + j] = __float2bfloat16(o[j]);
-          }
-        }
-        if (of_row) for (int j = 0; j < 16 && nb + 2 * j < N; ++j) of_row[ob + j] = o[j];
-        continue;
-      }
-      if (ep.act == TTB_ACT_GELU_NEW) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_new(v[j]);
-      } else if (ep.act == TTB_ACT_SILU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
-      } else if (ep.act == TTB_ACT_LRELU02) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = leaky(v[j], 0.2f);
-      }
-      const bool full = (nb + 32 <= N);
-      if (res_row) {
-        if (full && ((ep.ldr & 3) == 0)) {
-          const float4* rp = reinterpret_cast<const float4*>(res_row + nb);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 t = rp[j];
-            v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
-          }
-        } else {
-          for (int j = 0; j < 32 && nb + j < N; ++j) v[j] += res_row[nb + j];
-        }
-      }
-      if (of_row) {
-        if (full && ((ep.ldo & 3) == 0)) {
-          float4* dst = reinterpret_cast<float4*>(of_row + nb);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-          for (int j = 0; j < 32 && nb + j < N; ++j) of_row[nb + j] = v[j];
-        }
-      }
-      if (ob_row) {
-        if (full && ((ep.ldob & 7) == 0)) {
-          uint4* dst = reinterpret_cast<uint4*>(ob_row + nb);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-        } else {
-          for (int j = 0; j < 32 && nb + j < N; ++j) ob_row[nb + j] = __float2bfloat16(v[j]);
-        }
+        for (int c = 0; c < BN; c += 32)
+          if (n0 + c < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + c));
       }
     }
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    if (tr && threadIdx.x == 64) tr[5] = global_timer_ns();
+    // all MMAs have retired: the pipeline stages are idle and serve as the per-warp transpose scratch
+    gemm_epilogue_dispatch<BN>(tmem_base + ((uint32_t)(q * 32) << 16), n0, N, m0 + q * 32, M, lane, (long long)bz, ep,
+                               smem_u32(smem + (warp - 2) * EPI_SCRATCH_BYTES), nullptr);
     tc_fence_before();
+    if (tr && threadIdx.x == 64) tr[6] = global_timer_ns();
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<BN>(tmem_base);
   }
+  if (tr && threadIdx.x == 0) tr[7] = global_timer_ns();
 }
 
 // ------------------------------------------------------------------ reference (SIMT) GEMM: test/bring-up checker
@@ -331,6 +266,7 @@ __global__ void gemm_ref_kernel(const __nv_bfloat16* A, long long a_bstride, int
 }
 
 static int g_gemm_impl = -1;  // 0 = tcgen05, 1 = SIMT reference (bring-up only; TTB_GEMM_IMPL=ref)
+static unsigned long long* g_gemm_trace = nullptr;   // ttb_debug_gemm_trace
 
 template <int BN, int STAGES>
 static int launch_tc(const TtbGemmArgs& g, const GemmEpilogue& ep, cudaStream_t st) {
@@ -357,7 +293,8 @@ static int launch_tc(const TtbGemmArgs& g, const GemmEpilogue& ep, cudaStream_t 
   }
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, zdim);
   gemm_bf16_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, st>>>(ma, mb, g.M, g.N, g.K, g.taps, g.pad,
-                                                                        (bcast || g.splitk > 1) ? 0 : 1, kb_per_split, ep);
+                                                                        (bcast || g.splitk > 1) ? 0 : 1, kb_per_split, ep,
+                                                                        g_gemm_trace);
   TTB_CHECK_LAUNCH("gemm_bf16_tc_kernel");
   return 0;
 }
@@ -415,6 +352,11 @@ static int launch_persistent(const TtbGemmArgs& g, const GemmEpilogue& ep, cudaS
 }  // namespace ttb
 
 using namespace ttb;
+
+extern "C" int ttb_debug_gemm_trace(void* buf) {
+  g_gemm_trace = static_cast<unsigned long long*>(buf);
+  return 0;
+}
 
 extern "C" int ttb_gemm(const TtbGemmArgs* gp, void* stream) {
   const TtbGemmArgs& g = *gp;

@@ -1,100 +1,205 @@
-// Coalesced GEMM epilogue (included by gemm.cu after GemmEpilogue is defined).
+// GEMM epilogue shared by the tcgen05 GEMM kernels (included by gemm.cu after GemmEpilogue is defined).
 //
 // tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns). Writing that row straight to global
-// memory makes each warp-wide store touch 32 different cache lines with 16 bytes each: the LSU serialises them
-// (8x more transactions than needed) and the epilogue, not the tensor pipe, bounds every K<=1024 GEMM on the path
-// (ncu: tensor pipe 14-20 % active, long-scoreboard stalls; profiles/ncu_summary_r01_run10.txt).
-// Here the 32x32 chunk goes through a padded shared-memory tile so that 8 lanes cover one row's 128 bytes: a warp
-// instruction reads/writes 4 complete rows (4 x 128 B lines), for the residual read and the fp32 / bf16 writes alike.
+// memory makes each warp-wide store touch 32 different cache lines, so the 32x32 chunk goes through a padded
+// shared-memory tile: 8 lanes then cover one row's 128 bytes and a warp instruction moves 4 complete rows, for the
+// residual read and the fp32 / bf16 writes alike.
+//
+// Measured with ttb_debug_gemm_trace (profiles/gemm_trace_r01.txt): the first version of this epilogue -- one
+// function with every activation and every ragged-edge case behind run-time branches, inside the chunk loop -- took
+// ~2.3 us per 32-column chunk whatever it stored (9-10 us per 128x128 tile against a 5 us mainloop): the executed
+// path was spread over ~39 KB of code, and residual loads serialised behind possibly-aliasing stores. Hence:
+//   * the activation is a template parameter and the run-time switch sits OUTSIDE the chunk loop;
+//   * a chunk that is complete (32 rows, 32 columns, 16-byte aligned rows) takes a branch-free FAST path of ~100
+//     instructions; ragged edges take a separate, simple per-row SLOW path;
+//   * the residual (which may alias the output: x += f(x) in place) is loaded for the whole chunk before any store;
+//   * the transpose tile uses a 36-float pitch so both sides are conflict-free 128-bit shared accesses.
 #pragma once
 
 namespace ttb {
 
-constexpr int EPI_PITCH = 33;                       // floats per scratch row (bank-conflict-free column writes)
+constexpr int EPI_PITCH = 36;                           // floats per scratch row (144 B: 16-B aligned, conflict-free v4)
 constexpr int EPI_SCRATCH_BYTES = 32 * EPI_PITCH * 4;   // per epilogue warp
 
-// r: 32 accumulator columns [nb, nb+32) of row (m_base + lane). scratch: this warp's [32][33] float tile.
-TTB_DEVINL void gemm_epilogue_coalesced(const uint32_t* r, int nb, int N, int m_base, int M, int lane, long long bz,
-                                        const GemmEpilogue& ep, float* scratch) {
-  if (nb >= N) return;                               // warp-uniform
+TTB_DEVINL void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+TTB_DEVINL float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// tcgen05.wait::ld that also carries a data dependency on the loaded registers, so that no use of r[] can be scheduled
+// above the wait.
+TTB_DEVINL void tmem_ld_wait_dep(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+template <int ACT>
+TTB_DEVINL float epi_act(float x) {
+  if (ACT == TTB_ACT_GELU_NEW) return gelu_new(x);
+  if (ACT == TTB_ACT_SILU) return silu(x);
+  if (ACT == TTB_ACT_LRELU02) return leaky(x, 0.2f);
+  return x;
+}
+
+// What a tile's epilogue needs to know once (warp-uniform).
+struct EpiFlags {
+  bool aligned;     // bias pointer, ldr, ldo, ldob all allow 128-bit (fp32) / 64-bit (bf16) row accesses
+};
+
+TTB_DEVINL EpiFlags epi_flags(const GemmEpilogue& ep) {
+  EpiFlags f;
+  f.aligned = (!ep.bias || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0) &&
+              (!ep.residual || ((ep.ldr & 3) == 0 && (ep.res_bstride & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0)) &&
+              (!ep.out_f32 || ((ep.ldo & 3) == 0 && (ep.outf_bstride & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.out_f32) & 15) == 0)) &&
+              (!ep.out_bf16 || ((ep.ldob & 3) == 0 && (ep.outb_bstride & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.out_bf16) & 7) == 0));
+  return f;
+}
+
+// ---- FAST path: all 32 rows and 32 columns exist, everything aligned. Branch-free apart from the uniform pointer tests.
+template <int ACT>
+TTB_DEVINL void epi_chunk_fast(const uint32_t* r, int nb, int m_base, int lane, long long bz, const GemmEpilogue& ep,
+                               uint32_t scratch) {
+  const uint32_t wrow = scratch + (uint32_t)lane * (EPI_PITCH * 4);
   float v[32];
+  if (ep.bias) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float x = __uint_as_float(r[j]) * ep.alpha;
-    if (ep.bias && nb + j < N) x += __ldg(ep.bias + nb + j);
-    v[j] = x;
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + nb) + j);
+      v[4 * j] = fmaf(__uint_as_float(r[4 * j]), ep.alpha, b.x);
+      v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), ep.alpha, b.y);
+      v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), ep.alpha, b.z);
+      v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), ep.alpha, b.w);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
   }
-  if (ep.act == TTB_ACT_GEGLU) {
+  if (ACT == TTB_ACT_GEGLU) {
     // columns interleaved (u0,g0,u1,g1,...): out[j] = u * gelu_erf(g); output width N/2 -> 16 columns per chunk
 #pragma unroll
-    for (int j = 0; j < 16; ++j) scratch[lane * EPI_PITCH + j] = v[2 * j] * gelu_erf(v[2 * j + 1]);
+    for (int k = 0; k < 4; ++k)
+      sts128(wrow + k * 16, v[8 * k] * gelu_erf(v[8 * k + 1]), v[8 * k + 2] * gelu_erf(v[8 * k + 3]),
+             v[8 * k + 4] * gelu_erf(v[8 * k + 5]), v[8 * k + 6] * gelu_erf(v[8 * k + 7]));
     __syncwarp();
-    const int ob = nb >> 1, nout = N >> 1;
+    const int rr0 = lane >> 2, c = (lane & 3) * 4;   // 8 rows per instruction: 4 lanes x 4 columns per row
+    const long long col = (nb >> 1) + c;
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {                 // 8 rows per instruction: 4 lanes x 4 columns per row
-      const int rr = it * 8 + (lane >> 2), c = (lane & 3) * 4;
-      const int m = m_base + rr, n = ob + c;
-      if (m < M && n < nout) {
-        const float* s = scratch + rr * EPI_PITCH + c;
-        const float o0 = s[0], o1 = s[1], o2 = s[2], o3 = s[3];
-        if (ep.out_bf16) {
-          __nv_bfloat16* p = ep.out_bf16 + bz * ep.outb_bstride + (long long)m * ep.ldob + n;
-          if (n + 4 <= nout && (ep.ldob & 3) == 0) *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
-          else { const float o[4] = {o0, o1, o2, o3}; for (int j = 0; j < 4 && n + j < nout; ++j) p[j] = __float2bfloat16(o[j]); }
-        }
-        if (ep.out_f32) {
-          float* p = ep.out_f32 + bz * ep.outf_bstride + (long long)m * ep.ldo + n;
-          const float o[4] = {o0, o1, o2, o3};
-          for (int j = 0; j < 4 && n + j < nout; ++j) p[j] = o[j];
-        }
-      }
+    for (int it = 0; it < 4; ++it) {
+      const int rr = it * 8 + rr0;
+      const float4 o = lds128(scratch + (uint32_t)(rr * EPI_PITCH + c) * 4);
+      const long long m = m_base + rr;
+      if (ep.out_bf16)
+        *reinterpret_cast<uint2*>(ep.out_bf16 + bz * ep.outb_bstride + m * ep.ldob + col) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + bz * ep.outf_bstride + m * ep.ldo + col) = o;
     }
-    __syncwarp();
+    __syncwarp();                                    // scratch is reused by the next chunk
     return;
   }
-  if (ep.act == TTB_ACT_GELU_NEW) {
+  const int rr0 = lane >> 3, c = (lane & 7) * 4;     // 4 rows per instruction: 8 lanes x 4 columns per row
+  const long long col = nb + c;
+  // residual for the positions this lane stores, all issued before the first store
+  float4 rs[8];
+  if (ep.residual) {
+    const float* rp = ep.residual + bz * ep.res_bstride + (long long)(m_base + rr0) * ep.ldr + col;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_new(v[j]);
-  } else if (ep.act == TTB_ACT_SILU) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
-  } else if (ep.act == TTB_ACT_LRELU02) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = leaky(v[j], 0.2f);
+    for (int it = 0; it < 8; ++it) rs[it] = *reinterpret_cast<const float4*>(rp + (long long)it * 4 * ep.ldr);
   }
 #pragma unroll
-  for (int j = 0; j < 32; ++j) scratch[lane * EPI_PITCH + j] = v[j];
+  for (int k = 0; k < 8; ++k)
+    sts128(wrow + k * 16, epi_act<ACT>(v[4 * k]), epi_act<ACT>(v[4 * k + 1]), epi_act<ACT>(v[4 * k + 2]),
+           epi_act<ACT>(v[4 * k + 3]));
   __syncwarp();
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {                   // 4 rows per instruction: 8 lanes x 4 columns per row
-    const int rr = it * 4 + (lane >> 3), c = (lane & 7) * 4;
-    const int m = m_base + rr, n = nb + c;
-    if (m < M && n < N) {
-      const float* s = scratch + rr * EPI_PITCH + c;
-      float o[4] = {s[0], s[1], s[2], s[3]};
-      const bool full4 = (n + 4 <= N);
-      if (ep.residual) {
-        const float* p = ep.residual + bz * ep.res_bstride + (long long)m * ep.ldr + n;
-        if (full4 && (ep.ldr & 3) == 0) {
-          const float4 t = *reinterpret_cast<const float4*>(p);
-          o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
-        } else {
-          for (int j = 0; j < 4 && n + j < N; ++j) o[j] += p[j];
-        }
-      }
-      if (ep.out_f32) {
-        float* p = ep.out_f32 + bz * ep.outf_bstride + (long long)m * ep.ldo + n;
-        if (full4 && (ep.ldo & 3) == 0) *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
-        else for (int j = 0; j < 4 && n + j < N; ++j) p[j] = o[j];
-      }
-      if (ep.out_bf16) {
-        __nv_bfloat16* p = ep.out_bf16 + bz * ep.outb_bstride + (long long)m * ep.ldob + n;
-        if (full4 && (ep.ldob & 3) == 0) *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
-        else for (int j = 0; j < 4 && n + j < N; ++j) p[j] = __float2bfloat16(o[j]);
-      }
-    }
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + rr0;
+    float4 o = lds128(scratch + (uint32_t)(rr * EPI_PITCH + c) * 4);
+    if (ep.residual) { o.x += rs[it].x; o.y += rs[it].y; o.z += rs[it].z; o.w += rs[it].w; }
+    const long long m = m_base + rr;
+    if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + bz * ep.outf_bstride + m * ep.ldo + col) = o;
+    if (ep.out_bf16)
+      *reinterpret_cast<uint2*>(ep.out_bf16 + bz * ep.outb_bstride + m * ep.ldob + col) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
   }
   __syncwarp();                                      // scratch is reused by the next chunk
+}
+
+// ---- SLOW path (ragged M / N edges, unaligned rows): each lane finishes its own accumulator row with scalar accesses.
+template <int ACT>
+TTB_DEVINL void epi_chunk_slow(const uint32_t* r, int nb, int N, int m, int M, long long bz, const GemmEpilogue& ep) {
+  if (m >= M) return;
+  if (ACT == TTB_ACT_GEGLU) {
+    const int nout = N >> 1, ob = nb >> 1;
+    float* of = ep.out_f32 ? ep.out_f32 + bz * ep.outf_bstride + (long long)m * ep.ldo : nullptr;
+    __nv_bfloat16* obf = ep.out_bf16 ? ep.out_bf16 + bz * ep.outb_bstride + (long long)m * ep.ldob : nullptr;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (ob + j < nout) {
+        float u = __uint_as_float(r[2 * j]) * ep.alpha, g = __uint_as_float(r[2 * j + 1]) * ep.alpha;
+        if (ep.bias) { u += __ldg(ep.bias + nb + 2 * j); g += __ldg(ep.bias + nb + 2 * j + 1); }
+        const float o = u * gelu_erf(g);
+        if (of) of[ob + j] = o;
+        if (obf) obf[ob + j] = __float2bfloat16(o);
+      }
+    }
+    return;
+  }
+  const float* rp = ep.residual ? ep.residual + bz * ep.res_bstride + (long long)m * ep.ldr : nullptr;
+  float* of = ep.out_f32 ? ep.out_f32 + bz * ep.outf_bstride + (long long)m * ep.ldo : nullptr;
+  __nv_bfloat16* obf = ep.out_bf16 ? ep.out_bf16 + bz * ep.outb_bstride + (long long)m * ep.ldob : nullptr;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (nb + j < N) {
+      float x = __uint_as_float(r[j]) * ep.alpha;
+      if (ep.bias) x += __ldg(ep.bias + nb + j);
+      x = epi_act<ACT>(x);
+      if (rp) x += rp[nb + j];
+      if (of) of[nb + j] = x;
+      if (obf) obf[nb + j] = __float2bfloat16(x);
+    }
+  }
+}
+
+// Whole accumulator tile of one epilogue warp: taddr = TMEM address of (lane group, first column). When release_bar
+// is given it is arrived on once the last tcgen05.ld has completed (persistent kernel: the MMA warp may then overwrite
+// this accumulator buffer while the stores are still going out).
+template <int BN, int ACT>
+TTB_DEVINL void gemm_epilogue_tile(uint32_t taddr, int n0, int N, int m_base, int M, int lane, long long bz,
+                                   const GemmEpilogue& ep, uint32_t scratch, uint64_t* release_bar) {
+  constexpr int NCH = BN / 32;
+  const bool rows_full = epi_flags(ep).aligned && m_base + 32 <= M;
+  // rolled on purpose: one chunk's worth of code and registers (the 128-wide kernel must stay <= 168 registers for
+  // two CTAs per SM); the co-resident warps cover the tcgen05.ld latency
+#pragma unroll 1
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int nb = n0 + ch * 32;
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(taddr + (uint32_t)ch * 32, r);
+    tmem_ld_wait_dep(r);
+    if (release_bar && ch == NCH - 1) { tc_fence_before(); mbar_arrive(release_bar); }
+    if (nb >= N) continue;                           // warp-uniform
+    if (rows_full && nb + 32 <= N) epi_chunk_fast<ACT>(r, nb, m_base, lane, bz, ep, scratch);
+    else epi_chunk_slow<ACT>(r, nb, N, m_base + lane, M, bz, ep);
+  }
+}
+
+template <int BN>
+TTB_DEVINL void gemm_epilogue_dispatch(uint32_t taddr, int n0, int N, int m_base, int M, int lane, long long bz,
+                                       const GemmEpilogue& ep, uint32_t scratch, uint64_t* release_bar) {
+  switch (ep.act) {
+    case TTB_ACT_GEGLU: gemm_epilogue_tile<BN, TTB_ACT_GEGLU>(taddr, n0, N, m_base, M, lane, bz, ep, scratch, release_bar); break;
+    case TTB_ACT_GELU_NEW: gemm_epilogue_tile<BN, TTB_ACT_GELU_NEW>(taddr, n0, N, m_base, M, lane, bz, ep, scratch, release_bar); break;
+    case TTB_ACT_SILU: gemm_epilogue_tile<BN, TTB_ACT_SILU>(taddr, n0, N, m_base, M, lane, bz, ep, scratch, release_bar); break;
+    case TTB_ACT_LRELU02: gemm_epilogue_tile<BN, TTB_ACT_LRELU02>(taddr, n0, N, m_base, M, lane, bz, ep, scratch, release_bar); break;
+    default: gemm_epilogue_tile<BN, TTB_ACT_NONE>(taddr, n0, N, m_base, M, lane, bz, ep, scratch, release_bar); break;
+  }
 }
 
 }  // namespace ttb

@@ -115,23 +115,11 @@ gemm_bf16_tc_mc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     }
   } else {
     const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int m = m0 + row;
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    const bool row_ok = m < M;
-    const float* res_row = ep.residual ? ep.residual + (long long)bz * ep.res_bstride + (long long)m * ep.ldr : nullptr;
-    float* of_row = ep.out_f32 ? ep.out_f32 + (long long)bz * ep.outf_bstride + (long long)m * ep.ldo : nullptr;
-    __nv_bfloat16* ob_row = ep.out_bf16 ? ep.out_bf16 + (long long)bz * ep.outb_bstride + (long long)m * ep.ldob : nullptr;
-    float* scratch = reinterpret_cast<float*>(smem + (warp - 2) * EPI_SCRATCH_BYTES);   // stages are idle by now
-    (void)row_ok; (void)res_row; (void)of_row; (void)ob_row;
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-      tmem_ld_wait();
-      gemm_epilogue_coalesced(r, n0 + c, N, m0 + q * 32, M, lane, (long long)bz, ep, scratch);
-    }
+    // the pipeline stages are idle by now and serve as the transpose scratch
+    gemm_epilogue_dispatch<BN>(tmem_base + ((uint32_t)(q * 32) << 16), n0, N, m0 + q * 32, M, lane, (long long)bz, ep,
+                               smem_u32(smem + (warp - 2) * EPI_SCRATCH_BYTES), nullptr);
     tc_fence_before();
   }
   __syncthreads();

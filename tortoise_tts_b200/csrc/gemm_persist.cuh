@@ -179,33 +179,18 @@ gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const 
     }
   } else {
     const int q = warp & 3;
-    const int row = q * 32 + lane;
     int t = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
       const int mt = tile % m_tiles, rest = tile / m_tiles;
       const int nt = rest % n_tiles, bz = rest / n_tiles;
-      const int m = mt * BM + row, n0 = nt * BN;
+      const int n0 = nt * BN;
       const int acc = t & 1;
       mbar_wait(&acc_full[acc], (t >> 1) & 1);
       tc_fence_after();
-      const bool row_ok = m < M;
-      const float* res_row = ep.residual ? ep.residual + (long long)bz * ep.res_bstride + (long long)m * ep.ldr : nullptr;
-      float* of_row = ep.out_f32 ? ep.out_f32 + (long long)bz * ep.outf_bstride + (long long)m * ep.ldo : nullptr;
-      __nv_bfloat16* ob_row = ep.out_bf16 ? ep.out_bf16 + (long long)bz * ep.outb_bstride + (long long)m * ep.ldob : nullptr;
-      // pull the whole accumulator row into registers first, release the TMEM buffer, then do the memory-bound part
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), r);
-        tmem_ld_wait();
-        if (c + 32 >= BN) {          // last chunk read: the MMA warp may start overwriting this accumulator
-          tc_fence_before();
-          mbar_arrive(&acc_empty[acc]);
-        }
-        gemm_epilogue_coalesced(r, n0 + c, N, mt * BM + q * 32, M, lane, (long long)bz, ep,
-                                reinterpret_cast<float*>(smem + L::SCRATCH_OFF + (warp - 2) * EPI_SCRATCH_BYTES));
-      }
-      (void)row_ok; (void)res_row; (void)of_row; (void)ob_row;
+      // the accumulator buffer is handed back to the MMA warp as soon as its last tcgen05.ld has completed
+      gemm_epilogue_dispatch<BN>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN), n0, N, mt * BM + q * 32, M,
+                                 lane, (long long)bz, ep, smem_u32(smem + L::SCRATCH_OFF + (warp - 2) * EPI_SCRATCH_BYTES),
+                                 &acc_empty[acc]);
     }
   }
   __syncthreads();

@@ -54,7 +54,7 @@ SYMBOLS = [
     "ttb_ar_fix_codes", "ttb_embed", "ttb_clvp_rotary", "ttb_clvp_pool", "ttb_clvp_project",
     "ttb_timestep_embedding", "ttb_linear_small", "ttb_interp_nearest", "ttb_diffusion_step", "ttb_counter_add",
     "ttb_transpose_f32", "ttb_cast_pad_bf16", "ttb_broadcast_rows", "ttb_voc_conv1d", "ttb_voc_convt",
-    "ttb_voc_lvc_gate", "ttb_voc_to_tokens_bf16",
+    "ttb_voc_lvc_gate", "ttb_voc_to_tokens_bf16", "ttb_debug_gemm_trace",
 ]
 
 
@@ -127,6 +127,11 @@ def gemm(A, W, *, M, N, K, bias=None, residual=None, out_f32=None, out_bf16=None
     g.alpha, g.tile_n, g.force_ref, g.splitk, g.cluster = alpha, tile_n, 1 if force_ref else 0, splitk, cluster
     g.variant = variant
     _chk(load().ttb_gemm(C.byref(g), _stream()), "ttb_gemm")
+
+
+def debug_gemm_trace(buf):
+    """buf: int64 cuda tensor with 8 entries per CTA of the traced launches, or None to switch tracing off."""
+    load().ttb_debug_gemm_trace(_p(buf))
 
 
 def layernorm(x, M, D, g1, b1, g2=None, b2=None, out_bf16=None, out_f32=None):
