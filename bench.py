@@ -59,6 +59,16 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+_T0 = time.perf_counter()
+
+
+def progress(msg):
+    """stderr breadcrumbs (stdout carries only the JSON line): a run cut off by a timeout still says where it was."""
+    if os.environ.get("RANK", "0") == "0":
+        sys.stderr.write("[bench %7.1fs] %s\n" % (time.perf_counter() - _T0, msg))
+        sys.stderr.flush()
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -158,9 +168,12 @@ def run_engine(args):
     from tortoise_tts_b200.synth import synth_all
     from tortoise_tts_b200.api import TextToSpeech
     from tortoise_tts_b200 import lib
+    progress("extension built; synthesising the full-size checkpoint")
     cfg = ModelConfig.full()
     sds = synth_all(cfg, seed=0, suppress_stop=True)
+    progress("checkpoint ready; loading engines")
     tts = TextToSpeech(state_dicts=sds, config=cfg, kv_cache=True, device="cuda:%d" % local)
+    progress("engines ready")
     tokens = load_tokens(args.text)
     n_mel = args.mel_tokens
     g = torch.Generator().manual_seed(0)
@@ -180,6 +193,7 @@ def run_engine(args):
 
     for i in range(args.warmup):
         wav = step(i)
+        progress("warm-up %d done: %s" % (i, {k_: round(v, 1) for k_, v in tts.last_timings.items()}))
     sampler = ClockSampler(local)
     sampler.start()
     sync()
@@ -190,6 +204,7 @@ def run_engine(args):
     for i in range(args.steps):
         wav = step(args.warmup + i)
         dev_ms.append(tts.last_timings["device_total_ms"])
+        progress("timed step %d: %.1f ms on device" % (i, dev_ms[-1]))
         for k_, v in tts.last_timings.items():
             stage[k_] = stage.get(k_, 0.0) + v / args.steps
     sync()
@@ -228,14 +243,18 @@ def run_engine(args):
         "stage_ms": {k_: round(v, 2) for k_, v in stage.items()},
     }
     if world == 1:
+        progress("kernel probes")
         probes, how = kernel_probes(tts, cfg, n_mel, B, len(tokens) + 5)
+        progress("probes done")
         dom = max(probes, key=lambda d: d["total_ms_per_utterance"])
         line["roofline"] = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": round(dom["achieved"], 2),
                             "peak": dom["peak"], "unit": dom["unit"], "frac": round(dom["frac"], 4), "traffic": None,
                             "peak_source": how, "launch_ms": round(dom["ms"], 4)}
         line["kernels"] = [{k_: (round(v, 4) if isinstance(v, float) else v) for k_, v in d.items()} for d in probes]
         if not args.no_cpu_baseline:
+            progress("cpu baseline (oracle port on the host cores)")
             line["cpu_baseline"] = cpu_baseline(cfg, sds, tokens, B, n_mel, args)
+            progress("cpu baseline done")
     print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:
@@ -243,10 +262,18 @@ def run_engine(args):
 
 
 def cpu_baseline(cfg, sds, tokens, B, n_mel, args):
-    from oracle import cpu_baseline as cb
-    iters = {"standard": 200, "fast": 80, "ultra_fast": 30, "high_quality": 400}[args.preset]
-    r = cb.measure(cfg, sds, tokens + [0], num_candidates=B, n_mel=n_mel, iters=iters, cond_free=args.preset != "ultra_fast",
-                   threads=os.cpu_count())
+    # child process under a timeout: the oracle's thread pool must not inherit this process's CUDA-side state, and a
+    # host whose CPU quota misbehaves must not take the GPU arm's JSON line down with it
+    cmd = [sys.executable, "-m", "oracle.cpu_baseline", "--preset", args.preset, "--mel-tokens", str(n_mel),
+           "--tokens-json", os.path.join(ROOT, "tests", "golden", "bench_text_tokens.json"), "--text", args.text]
+    try:
+        out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=args.cpu_timeout)
+        r = json.loads(out.stdout.strip().splitlines()[-1])
+    except subprocess.TimeoutExpired:
+        return {"value": None, "unit": UNIT, "cores": None, "kind": "port",
+                "sample": "not finished within %d s on this host" % args.cpu_timeout}
+    except (ValueError, IndexError):
+        return {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": "failed: " + out.stderr[-300:]}
     return {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
             "total_s_extrapolated": round(r["total_s"], 1), "units_s": {k: round(v, 4) for k, v in r["units"].items()}}
 
@@ -257,22 +284,33 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    from tortoise_tts_b200.config import ModelConfig
-    from tortoise_tts_b200.synth import synth_all
-    cfg = ModelConfig.full()
-    sds = synth_all(cfg, seed=0, suppress_stop=True)
     tokens = load_tokens(args.text)
-    B = 256 if args.preset in ("standard", "high_quality") else (96 if args.preset == "fast" else 16)
-    vals = []
-    last = None
+    n = args.warmup + args.steps
+    # one child process takes all W+K samples (checkpoint synthesis and the thread-count probe are paid once); each
+    # sample is the bounded unit-cost measurement of oracle/cpu_baseline.py (~20-40 s of CPU work)
+    cmd = [sys.executable, "-m", "oracle.cpu_baseline", "--preset", args.preset, "--mel-tokens", str(args.mel_tokens),
+           "--tokens-json", os.path.join(ROOT, "tests", "golden", "bench_text_tokens.json"), "--text", args.text,
+           "--repeat", str(n)]
     t0 = time.perf_counter()
-    for i in range(args.warmup + args.steps):
-        last = cpu_baseline(cfg, sds, tokens, B, args.mel_tokens, args)
-        if i >= args.warmup:
-            vals.append(last["value"])
+    samples = []
+    try:
+        out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=args.cpu_timeout * n)
+        txt, err = out.stdout, out.stderr
+    except subprocess.TimeoutExpired as e:
+        txt = e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
+        err = "timeout after %d s" % (args.cpu_timeout * n)
+    for ln in txt.strip().splitlines():
+        try:
+            samples.append(json.loads(ln))
+        except ValueError:
+            pass
     wall = time.perf_counter() - t0
-    v = sum(vals) / len(vals)
+    timed = samples[args.warmup:] if len(samples) > args.warmup else samples[-1:]
+    if not timed:
+        print(json.dumps({"impl": "reference", "unavailable": "CPU oracle produced no sample: " + err[-200:].replace("\n", " ")}))
+        return
+    last = timed[-1]
+    v = sum(s["value"] for s in timed) / len(timed)
     audio_s = (args.mel_tokens * 4 * 24000 // 22050) * 256 / 24000.0
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": audio_s / v * 1e3, "higher_is_better": True,
@@ -296,6 +334,7 @@ def main():
     ap.add_argument("--mel-tokens", type=int, default=430)
     ap.add_argument("--preset-override", default=None, help="JSON dict of tts kwargs (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-timeout", type=int, default=240, help="seconds allowed per CPU-oracle sample")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

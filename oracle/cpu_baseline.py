@@ -16,6 +16,49 @@ import torch
 from . import ar, clvp, diffusion as od, vocoder as ov
 
 
+def host_threads(cap=64):
+    """CPU threads this process may really use: the affinity mask and the cgroup CPU quota, not os.cpu_count() (on a
+    shared box that is the machine's core count; handing it to OpenMP oversubscribes the quota by 10x+ and the spin-
+    waiting workers make every matmul crawl -- the first GPU-box run of this baseline never finished for that reason)."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        try:                                   # cgroup v1
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:
+                quota = int(f.read())
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                period = int(f.read())
+            if quota > 0:
+                n = min(n, max(1, quota // period))
+        except (OSError, ValueError):
+            pass
+    return max(1, min(n, cap))
+
+
+def pick_threads():
+    """The thread count that is actually fastest here: a quota the files above do not show still oversubscribes, so
+    time a 1536^3 fp32 matmul at the detected count and at a few smaller ones and keep the best."""
+    a = torch.randn(1536, 1536)
+    best_n, best_t = 1, 1e30
+    for n in sorted({host_threads(), 32, 16, 8, 4}):
+        if n > host_threads():
+            continue
+        torch.set_num_threads(n)
+        torch.mm(a, a)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            torch.mm(a, a)
+        t = time.perf_counter() - t0
+        if t < best_t * 0.9:                   # prefer fewer threads unless clearly slower
+            best_n, best_t = n, t
+    return best_n
+
+
 def _t(fn, reps=1):
     best = 1e30
     for _ in range(reps):
@@ -88,3 +131,42 @@ def measure(cfg, sds, text_tokens, num_candidates=256, n_mel=430, iters=200, con
               (decode_steps, clvp_rows, S))
     return dict(total_s=total, audio_s=audio_s, value=audio_s / total, units=units, sample=sample,
                 cores=torch.get_num_threads())
+
+
+def main():
+    """`python -m oracle.cpu_baseline --preset standard --mel-tokens 430 --tokens-json <file> --text para53`
+    prints one JSON object; bench.py runs this in a child process under a timeout so that the GPU arm's JSON line
+    never depends on how the host's CPU quota behaves."""
+    import argparse
+    import json
+    import os
+    import sys
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--preset", default="standard")
+    ap.add_argument("--mel-tokens", type=int, default=430)
+    ap.add_argument("--tokens-json", required=True)
+    ap.add_argument("--text", default="para53")
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--repeat", type=int, default=1, help="samples to take (one JSON line each)")
+    a = ap.parse_args()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from tortoise_tts_b200.config import ModelConfig
+    from tortoise_tts_b200.synth import synth_all
+    cfg = ModelConfig.full()
+    sds = synth_all(cfg, seed=0, suppress_stop=True)
+    with open(a.tokens_json) as f:
+        tokens = json.load(f)[a.text]["tokens"]
+    B = 256 if a.preset in ("standard", "high_quality") else (96 if a.preset == "fast" else 16)
+    iters = {"standard": 200, "fast": 80, "ultra_fast": 30, "high_quality": 400}[a.preset]
+    threads = a.threads or pick_threads()
+    for _ in range(a.repeat):
+        r = measure(cfg, sds, tokens + [0], num_candidates=B, n_mel=a.mel_tokens, iters=iters,
+                    cond_free=a.preset != "ultra_fast", threads=threads)
+        print(json.dumps(r))
+        sys.stdout.flush()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,4 +1,5 @@
 """Builds libttb.so (the sm_100a kernel library behind include/ttb.h) in-tree with nvcc."""
+import hashlib
 import os
 import subprocess
 import sys
@@ -6,21 +7,27 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libttb.so")
+STAMP = LIB + ".stamp"      # content hash of the sources the library was built from (travels with the .so)
 SOURCES = ["capi.cu", "gemm.cu", "norm.cu", "attention.cu", "flash_attn.cu", "ar.cu", "misc.cu", "vocoder.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
 
 
-def _newest_source_mtime():
-    m = 0.0
-    for f in os.listdir(CSRC):
-        m = max(m, os.path.getmtime(os.path.join(CSRC, f)))
-    m = max(m, os.path.getmtime(os.path.join(HERE, "..", "include", "ttb.h")))
-    return m
+def _source_hash():
+    """Hash of every file under csrc/ + the public header + the flags. File times are not used: a copy of the tree
+    (the GPU box receives one) need not preserve them, and a spurious rebuild costs minutes there."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(HERE, "..", "include", "ttb.h")]
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
 
 
 def build(force=False, verbose=False):
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source_mtime():
+    want = _source_hash()
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == want:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
@@ -41,6 +48,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed")
     cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
+    with open(STAMP, "w") as f:
+        f.write(want + "\n")
     return LIB
 
 

@@ -317,7 +317,7 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int PSTAGES>
+template <int BN, int PSTAGES, int EW>
 static int launch_persistent(const TtbGemmArgs& g, const GemmEpilogue& ep, cudaStream_t st) {
   CUtensorMap ma, mb;
   const bool bcast = (g.batch == 1) || (g.a_bstride == 0);
@@ -326,10 +326,10 @@ static int launch_persistent(const TtbGemmArgs& g, const GemmEpilogue& ep, cudaS
   if (get_tensor_map_bf16(&ma, g.A, (uint64_t)g.K, (uint64_t)g.rows, a_d2, (uint64_t)g.lda, a_s2, BK, BM)) return -1;
   if (get_tensor_map_bf16(&mb, g.W, (uint64_t)g.K * g.taps, (uint64_t)g.N, 1, (uint64_t)g.K * g.taps,
                           (uint64_t)g.K * g.taps * g.N, BK, BN)) return -1;
-  using L = GemmPSmem<BN, PSTAGES>;
+  using L = GemmPSmem<BN, PSTAGES, EW>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_persistent_kernel<BN, PSTAGES>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_persistent_kernel<BN, PSTAGES, EW>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm persistent)");
     attr_set = true;
@@ -343,7 +343,7 @@ static int launch_persistent(const TtbGemmArgs& g, const GemmEpilogue& ep, cudaS
   const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
   const long long total = (long long)m_tiles * n_tiles * zdim;
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  gemm_bf16_tc_persistent_kernel<BN, PSTAGES><<<grid, GEMM_THREADS, L::TOTAL, st>>>(
+  gemm_bf16_tc_persistent_kernel<BN, PSTAGES, EW><<<grid, 64 + 32 * EW, L::TOTAL, st>>>(
       ma, mb, g.M, g.N, g.K, g.taps, g.pad, (bcast || g.splitk > 1) ? 0 : 1, kb_per_split, m_tiles, n_tiles, zdim, ep);
   TTB_CHECK_LAUNCH("gemm_bf16_tc_persistent_kernel");
   return 0;
@@ -408,16 +408,16 @@ extern "C" int ttb_gemm(const TtbGemmArgs* gp, void* stream) {
   // (CLVP: 131 -> 90 ms; diffusion qkv conv 66 -> 50 us) and loses on the skinny decode GEMMs (one wave of tiny tiles,
   // where 2-4 resident CTAs per SM hide latency better than one deep pipeline), so it is used for >= 2 waves only.
   if (g.variant == 2) {
-    if (g.tile_n == 32) return launch_persistent<32, 8>(g, ep, st);
-    if (g.tile_n == 64) return launch_persistent<64, 8>(g, ep, st);
-    return launch_persistent<128, 6>(g, ep, st);
+    if (g.tile_n == 32) return launch_persistent<32, 8, 4>(g, ep, st);
+    if (g.tile_n == 64) return launch_persistent<64, 8, 4>(g, ep, st);
+    return launch_persistent<128, 6, 4>(g, ep, st);
   }
   const int use_persist = (g.variant == 1) ? 0 : persist;
-  if (use_persist && g.tile_n == 0 && tiles128 >= 2 * 148) return launch_persistent<128, 6>(g, ep, st);
+  if (use_persist && g.tile_n == 0 && tiles128 >= 2 * 148) return launch_persistent<128, 6, 4>(g, ep, st);
   if (use_persist == 2) {        // TTB_GEMM_PERSIST=2: force the persistent kernels everywhere (experiments)
-    if (g.tile_n == 32) return launch_persistent<32, 8>(g, ep, st);
-    if (g.tile_n == 64 || (g.tile_n == 0 && tiles128 < 148)) return launch_persistent<64, 8>(g, ep, st);
-    if (g.tile_n != 256) return launch_persistent<128, 6>(g, ep, st);
+    if (g.tile_n == 32) return launch_persistent<32, 8, 4>(g, ep, st);
+    if (g.tile_n == 64 || (g.tile_n == 0 && tiles128 < 148)) return launch_persistent<64, 8, 4>(g, ep, st);
+    if (g.tile_n != 256) return launch_persistent<128, 6, 4>(g, ep, st);
   }
   if (g.tile_n == 32) return launch_tc<32, 4>(g, ep, st);
   if (g.tile_n == 64 || (g.tile_n == 0 && tiles128 < 148)) return launch_tc<64, 4>(g, ep, st);

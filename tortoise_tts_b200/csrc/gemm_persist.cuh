@@ -4,103 +4,34 @@
 //   * the TMA -> MMA pipeline (PSTAGES deep) never drains between tiles,
 //   * the accumulator is double-buffered in TMEM (2 x BN columns): the epilogue of tile t overlaps the MMAs of t+1,
 //   * barrier init / TMEM allocation / descriptor prefetch are paid once per CTA instead of once per tile.
-// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue.
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..2+EW-1 = epilogue. With EW = 8 two warps
+// share each TMEM lane quarter and split the tile's columns: measured (profiles/gemm_trace_r01.txt) a 4-warp epilogue
+// needs ~4.9 us per 128x128 tile while the mainloop alone needs ~2.5 us, so with 4 warps the epilogue, not the tensor
+// pipe, set the pace of the persistent loop.
 #pragma once
 
 namespace ttb {
 
-template <int BN, int PSTAGES>
+template <int BN, int PSTAGES, int EW>
 struct GemmPSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = PSTAGES * STAGE_BYTES;
-  static constexpr int SCRATCH_OFF = BAR_OFF + (2 * PSTAGES + 4) * 8 + 16;   // 4 epilogue warps x [32][33] floats
-  static constexpr int TOTAL = SCRATCH_OFF + 4 * EPI_SCRATCH_BYTES + 1024;
+  static constexpr int SCRATCH_OFF = BAR_OFF + (2 * PSTAGES + 4) * 8 + 16;   // EW epilogue warps x transpose tile
+  static constexpr int TOTAL = SCRATCH_OFF + EW * EPI_SCRATCH_BYTES + 1024;
+  static_assert(TOTAL <= 227 * 1024, "persistent GEMM shared memory");
 };
 
-// epilogue of one 32-column chunk held in registers (thread = one output row)
-TTB_DEVINL void gemm_epilogue_chunk(const uint32_t* r, int nb, int N, const GemmEpilogue& ep, const float* res_row,
-                                    float* of_row, __nv_bfloat16* ob_row) {
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float x = __uint_as_float(r[j]) * ep.alpha;
-    if (ep.bias && nb + j < N) x += __ldg(ep.bias + nb + j);
-    v[j] = x;
-  }
-  if (ep.act == TTB_ACT_GEGLU) {
-    float o[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf(v[2 * j + 1]);
-    const int ob = nb >> 1;
-    if (ob_row) {
-      if (nb + 32 <= N) {
-        uint4* dst = reinterpret_cast<uint4*>(ob_row + ob);
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-          dst[j] = make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
-                              pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
-      } else {
-        for (int j = 0; j < 16 && nb + 2 * j < N; ++j) ob_row[ob + j] = __float2bfloat16(o[j]);
-      }
-    }
-    if (of_row) for (int j = 0; j < 16 && nb + 2 * j < N; ++j) of_row[ob + j] = o[j];
-    return;
-  }
-  if (ep.act == TTB_ACT_GELU_NEW) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_new(v[j]);
-  } else if (ep.act == TTB_ACT_SILU) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
-  } else if (ep.act == TTB_ACT_LRELU02) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = leaky(v[j], 0.2f);
-  }
-  const bool full = (nb + 32 <= N);
-  if (res_row) {
-    if (full && ((ep.ldr & 3) == 0)) {
-      const float4* rp = reinterpret_cast<const float4*>(res_row + nb);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 t = rp[j];
-        v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
-      }
-    } else {
-      for (int j = 0; j < 32 && nb + j < N; ++j) v[j] += res_row[nb + j];
-    }
-  }
-  if (of_row) {
-    if (full && ((ep.ldo & 3) == 0)) {
-      float4* dst = reinterpret_cast<float4*>(of_row + nb);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    } else {
-      for (int j = 0; j < 32 && nb + j < N; ++j) of_row[nb + j] = v[j];
-    }
-  }
-  if (ob_row) {
-    if (full && ((ep.ldob & 7) == 0)) {
-      uint4* dst = reinterpret_cast<uint4*>(ob_row + nb);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                            pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-    } else {
-      for (int j = 0; j < 32 && nb + j < N; ++j) ob_row[nb + j] = __float2bfloat16(v[j]);
-    }
-  }
-}
-
-template <int BN, int PSTAGES>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int PSTAGES, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                int M, int N, int K, int taps, int pad, int a_batch_mul, int kb_per_split, int m_tiles,
                                int n_tiles, int z_tiles, GemmEpilogue ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  using L = GemmPSmem<BN, PSTAGES>;
+  using L = GemmPSmem<BN, PSTAGES, EW>;
+  static_assert(EW == 4 || (EW == 8 && BN >= 64), "epilogue warps");
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* empty_bar = full_bar + PSTAGES;
   uint64_t* acc_full = empty_bar + PSTAGES;     // [2] MMA -> epilogue
@@ -117,7 +48,7 @@ gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const 
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < PSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 32 * EW); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
@@ -188,9 +119,11 @@ gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const 
       mbar_wait(&acc_full[acc], (t >> 1) & 1);
       tc_fence_after();
       // the accumulator buffer is handed back to the MMA warp as soon as its last tcgen05.ld has completed
-      gemm_epilogue_dispatch<BN>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN), n0, N, mt * BM + q * 32, M,
-                                 lane, (long long)bz, ep, smem_u32(smem + L::SCRATCH_OFF + (warp - 2) * EPI_SCRATCH_BYTES),
-                                 &acc_empty[acc]);
+      constexpr int BNW = BN / (EW / 4);               // columns per epilogue warp
+      const int cg = (warp - 2) >> 2;                  // column group of this warp (0 when EW == 4)
+      gemm_epilogue_dispatch<BNW>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cg * BNW), n0 + cg * BNW, N,
+                                  mt * BM + q * 32, M, lane, (long long)bz, ep,
+                                  smem_u32(smem + L::SCRATCH_OFF + (warp - 2) * EPI_SCRATCH_BYTES), &acc_empty[acc]);
     }
   }
   __syncthreads();
