@@ -47,7 +47,8 @@ typedef struct TtbGemmArgs {
                            (outf_bstride = stride between splits); batch must be 1, no epilogue fusion */
   int cluster;          /* 2 or 4: CTAs adjacent in N form a cluster and share the activation tile by TMA multicast
                            (tile_n picks the tile width: 32, 64, else 128); 0/1 = off */
-  int variant;          /* 0 = auto; 1 = one tile per CTA; 2 = persistent kernel (tools/gemm_sweep.py) */
+  int variant;          /* 0 = auto; 1 = one tile per CTA; 2 = persistent kernel; with tile_n = 32 also 3 / 4 = one tile
+                           per CTA with a 5- / 4-stage pipeline (tools/gemm_sweep.py, tools/gemm_diag.py) */
 } TtbGemmArgs;
 
 /* nn.Linear / HF Conv1D / nn.Conv1d(k=1,3) as one tcgen05 GEMM with fused bias/activation/residual.
@@ -79,7 +80,11 @@ int ttb_rmsnorm(const float* x, int M, int D, const float* g, void* out_bf16, vo
  * ResBlock / AttentionBlock (diffusion_decoder.py:107-120): y = GN(x)*gamma+beta; if scale_shift:
  * y = y*(1+scale[b,c]) + shift[b,c] (scale_shift fp32 [B, 2C] = [scale|shift]; when ss_row != NULL the table
  * row *ss_row (device-side step counter) at stride ss_row_stride is used); if silu: y = SiLU(y).
- * `partials` is a scratch buffer of B*groups*splits*2 floats. Output bf16 [B, S, ldo] and/or fp32. */
+ * `partials` is a scratch buffer of TTB_GROUPNORM_SCRATCH_FLOATS(B, groups) floats (per-block partial sums between
+ * the statistics and the apply kernel; nothing is kept across calls, so one buffer may serve any number of calls on
+ * the same stream). Results are bit-reproducible (no atomics). Output bf16 [B, S, ldo] and/or fp32. */
+#define TTB_GROUPNORM_SPLITS 128
+#define TTB_GROUPNORM_SCRATCH_FLOATS(B, groups) ((B) * (groups) * (2 * TTB_GROUPNORM_SPLITS + 2) + 16)
 int ttb_groupnorm(const float* x, int B, int S, int C, int groups, const float* gamma, const float* beta,
                   const float* scale_shift, int ss_bstride, const int* ss_row, int ss_row_stride, int silu,
                   float* partials, void* out_bf16, int ldo, float* out_f32, int ldof, void* stream);

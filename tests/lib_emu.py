@@ -82,6 +82,10 @@ def rmsnorm(x, M, D, g, out_bf16):
     _v(out_bf16, (M, D), (D, 1)).copy_((xx / norm.clamp(min=1e-8) * g).to(torch.bfloat16))
 
 
+def groupnorm_scratch(B, groups, device):
+    return torch.zeros(B * groups * (2 * 128 + 2) + 16, dtype=torch.float32, device=device)
+
+
 def groupnorm(x, B, S, Cc, groups, gamma, beta, partials, scale_shift=None, ss_bstride=0, ss_row=None, ss_row_stride=0,
               silu=False, out_bf16=None, ldo=0, out_f32=None, ldof=0):
     xx = _v(x, (B, S, Cc), (S * Cc, Cc, 1)).transpose(1, 2)

@@ -90,6 +90,10 @@ def main():
         kw = dict(M=M, N=N, K=K, taps=taps, pad=(taps - 1) // 2, batch=batch, a_bstride=M * K, res_bstride=M * N,
                   outf_bstride=M * N, outb_bstride=M * N)
         tiles = [32] if M <= 256 else [64, 128]
+        if M <= 256:          # one-tile kernel, 5 stages (variant 3) against 4 stages (variant 4)
+            for v, nm in ((3, "5 stages"), (4, "4 stages")):
+                t1 = per_launch_us(lambda: lib.gemm(A, W, bias=bias, out_bf16=ob, tile_n=32, variant=v, **kw))
+                print("   tile  32 one-tile %s: %.1f us" % (nm, t1))
         for tile in tiles:
             for variant in (1, 2):
                 full = lambda: lib.gemm(A, W, bias=bias, residual=of if res else None, out_f32=of, out_bf16=ob,

@@ -419,7 +419,13 @@ extern "C" int ttb_gemm(const TtbGemmArgs* gp, void* stream) {
     if (g.tile_n == 64 || (g.tile_n == 0 && tiles128 < 148)) return launch_persistent<64, 8, 4>(g, ep, st);
     if (g.tile_n != 256) return launch_persistent<128, 6, 4>(g, ep, st);
   }
-  if (g.tile_n == 32) return launch_tc<32, 4>(g, ep, st);
+  if (g.tile_n == 32) {
+    // the skinny decode GEMMs are latency-bound (k-block time = TMA round trip / stages): 5 stages still allow two
+    // CTAs per SM (2 x 100 KB). TTB_GEMM_T32_STAGES=4 restores the 4-stage kernel for A/B runs; variant 3 forces 5.
+    static int t32 = -1;
+    if (t32 < 0) { const char* e = getenv("TTB_GEMM_T32_STAGES"); t32 = e ? atoi(e) : 5; }
+    return (g.variant == 3 || (g.variant != 4 && t32 == 5)) ? launch_tc<32, 5>(g, ep, st) : launch_tc<32, 4>(g, ep, st);
+  }
   if (g.tile_n == 64 || (g.tile_n == 0 && tiles128 < 148)) return launch_tc<64, 4>(g, ep, st);
   // large problems are L2-bandwidth bound with 128x128 tiles (64 flop/B at ~6.3 KB/clk of L2): 128x256 tiles raise the
   // intensity to 85 flop/B when the grid still covers most SMs

@@ -168,6 +168,129 @@ gn_apply_kernel(const float* __restrict__ x, int S, int C, int groups, int cpg, 
   if (of) *reinterpret_cast<float4*>(of + ((long long)b * S + srow) * ldof + c) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Row-wise GroupNorm (the path the denoiser takes: C = 1024, 32 groups). The two kernels above walk one GROUP at a
+// time (128-byte segments 4 KB apart) and re-derive every per-channel constant for each float4; the ncu launch list
+// of a denoiser step (profiles/ncu_launches_r01_diffusion_step.txt) had them at 9.7 + 13.6 us per GroupNorm, i.e.
+// 1.6 TB/s on 15 MB, and 23 % of the step. Here a block owns whole ROWS (4 KB contiguous), thread t owns the float4
+// column t of every row of its block:
+//   stats: per-thread (sum, sumsq) over the block's rows, xor-shuffle over the cpg/4 lanes of a group, then a fixed-order
+//          sum over the block's row lanes in shared memory: one partial per (batch, group, block). No atomics anywhere:
+//          the result must be bit-identical from run to run (the DDPM loop amplifies a last-bit difference in eps
+//          153-fold, and the CUDA-graph and eager paths are tested for equality);
+//   apply: the cpg/4 lanes of a group share out the group's partials (all loads in flight at once), shuffle-reduce them
+//          to (mean, rstd), fold mean/rstd/gamma/beta/scale/shift of their 4 channels into y = x * a + b ONCE, then
+//          stream their rows: one 16-byte load, 4 FMAs (+ SiLU), one 8-byte bf16 (and/or 16-byte fp32) store per row.
+//          (A "last block folds the partials" variant of the stats kernel was measured slower: its serial tail sat on
+//          the critical path of every GroupNorm.)
+// scratch layout (floats): 16 unused | [B][groups][TTB_GN_SPLITS][2] partial sums.
+__global__ void __launch_bounds__(256)
+gn_stats_rows_kernel(const float* __restrict__ x, int B, int S, int C, int groups, int cpg, int tpr, int rows_per,
+                     int splits, float* __restrict__ scratch) {
+  __shared__ float sacc[2 * 256];                               // [row lane][group][2]; rows_par * groups = 256 / lpg
+  const int sp = blockIdx.x, b = blockIdx.y;
+  const int rows_par = 256 / tpr;
+  const int rl = threadIdx.x / tpr, ct = threadIdx.x - rl * tpr;
+  const int s0 = sp * rows_per, s1 = min(S, s0 + rows_per);
+  const float* xp = x + (long long)b * S * C + ct * 4;
+  float s = 0.f, q = 0.f;
+  int r = s0 + rl;
+  for (; r + 7 * rows_par < s1; r += 8 * rows_par) {           // 8 independent 16-byte loads in flight per thread
+    float4 t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t[u] = *reinterpret_cast<const float4*>(xp + (long long)(r + u * rows_par) * C);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      s += (t[u].x + t[u].y) + (t[u].z + t[u].w);
+      q += (t[u].x * t[u].x + t[u].y * t[u].y) + (t[u].z * t[u].z + t[u].w * t[u].w);
+    }
+  }
+  for (; r < s1; r += rows_par) {
+    const float4 t = *reinterpret_cast<const float4*>(xp + (long long)r * C);
+    s += (t.x + t.y) + (t.z + t.w);
+    q += (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w);
+  }
+  const int lpg = cpg >> 2;                                     // lanes per group: power of two <= min(32, tpr)
+  for (int off = lpg >> 1; off > 0; off >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, off);
+    q += __shfl_xor_sync(0xffffffffu, q, off);
+  }
+  if ((ct & (lpg - 1)) == 0) {                                  // exactly one writer per (row lane, group)
+    const int g = (ct * 4) / cpg;
+    sacc[(rl * groups + g) * 2] = s;
+    sacc[(rl * groups + g) * 2 + 1] = q;
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < groups; g += 256) {
+    float su = 0.f, sq = 0.f;
+    for (int k = 0; k < rows_par; ++k) { su += sacc[(k * groups + g) * 2]; sq += sacc[(k * groups + g) * 2 + 1]; }
+    float* p = scratch + 16 + (((long long)b * groups + g) * TTB_GN_SPLITS + sp) * 2;
+    p[0] = su;
+    p[1] = sq;
+  }
+  (void)B; (void)splits;
+}
+
+__global__ void __launch_bounds__(256)
+gn_apply_rows_kernel(const float* __restrict__ x, int S, int C, int groups, int cpg, int tpr, int rows_per, int splits,
+                     const float* __restrict__ scratch, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const float* __restrict__ ss, int ss_bstride, const int* __restrict__ ss_row, int ss_row_stride,
+                     int do_silu, __nv_bfloat16* __restrict__ ob, int ldo, float* __restrict__ of, int ldof) {
+  const int b = blockIdx.y;
+  const int rows_par = 256 / tpr;
+  const int rl = threadIdx.x / tpr, ct = threadIdx.x - rl * tpr;
+  const int c = ct * 4;
+  const int g = c / cpg;
+  // (mean, rstd) of this thread's group: the group's lanes take every lpg-th partial each, then a fixed xor tree
+  const int lpg = cpg >> 2, sub = ct & (lpg - 1);
+  const float2* part = reinterpret_cast<const float2*>(scratch + 16) + ((long long)b * groups + g) * TTB_GN_SPLITS;
+  float su = 0.f, sq = 0.f;
+  for (int k = sub; k < splits; k += lpg) {
+    const float2 p = part[k];
+    su += p.x;
+    sq += p.y;
+  }
+  for (int off = lpg >> 1; off > 0; off >>= 1) {
+    su += __shfl_xor_sync(0xffffffffu, su, off);
+    sq += __shfl_xor_sync(0xffffffffu, sq, off);
+  }
+  const float n = (float)S * (float)cpg;
+  const float mean = su / n;
+  const float rstd = rsqrtf(fmaxf(sq / n - mean * mean, 0.f) + 1e-5f);
+  float a[4], o[4];
+  if (ss && ss_row) ss += (long long)(*ss_row) * ss_row_stride;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    a[j] = rstd * __ldg(gamma + c + j);
+    o[j] = __ldg(beta + c + j) - mean * a[j];
+    if (ss) {
+      const float sc = 1.0f + ss[(long long)b * ss_bstride + c + j], sh = ss[(long long)b * ss_bstride + C + c + j];
+      a[j] *= sc;
+      o[j] = o[j] * sc + sh;
+    }
+  }
+  const int s0 = blockIdx.x * rows_per, s1 = min(S, s0 + rows_per);
+  const float* xp = x + (long long)b * S * C + c;
+  for (int r0 = s0 + rl; r0 < s1; r0 += 8 * rows_par) {
+    float4 t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = r0 + u * rows_par;
+      if (r < s1) t[u] = *reinterpret_cast<const float4*>(xp + (long long)r * C);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = r0 + u * rows_par;
+      if (r >= s1) break;
+      float y0 = fmaf(t[u].x, a[0], o[0]), y1 = fmaf(t[u].y, a[1], o[1]), y2 = fmaf(t[u].z, a[2], o[2]),
+            y3 = fmaf(t[u].w, a[3], o[3]);
+      if (do_silu) { y0 = silu(y0); y1 = silu(y1); y2 = silu(y2); y3 = silu(y3); }
+      if (ob) *reinterpret_cast<uint2*>(ob + ((long long)b * S + r) * ldo + c) = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+      if (of) *reinterpret_cast<float4*>(of + ((long long)b * S + r) * ldof + c) = make_float4(y0, y1, y2, y3);
+    }
+  }
+}
+
 }  // namespace ttb
 using namespace ttb;
 
@@ -213,8 +336,29 @@ extern "C" int ttb_groupnorm(const float* x, int B, int S, int C, int groups, co
   if (C % groups != 0 || (C & 3)) { set_error("ttb_groupnorm: C=%d groups=%d unsupported", C, groups); return -1; }
   const int cpg = C / groups;
   if (cpg % 4 != 0 && (cpg & 3)) { set_error("ttb_groupnorm: channels per group must be a multiple of 4"); return -1; }
-  const int splits = TTB_GN_SPLITS;
+  auto is_pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+  const int cols = C >> 2, lpg = cpg >> 2;
+  const char* impl = getenv("TTB_GN_IMPL");       // "group" forces the generic group-wise kernels (A/B timing)
+  const bool force_group = impl && impl[0] == 'g';
+  if (!force_group && (cpg & 3) == 0 && is_pow2(cols) && cols <= 256 && is_pow2(lpg) && lpg <= 32 && groups <= 256 && S > 0) {
+    // row-wise path (see gn_stats_rows_kernel)
+    const int tpr = cols, rows_par = 256 / tpr;
+    int splits = (S + 8 * rows_par - 1) / (8 * rows_par);
+    splits = splits < 1 ? 1 : (splits > TTB_GN_SPLITS ? TTB_GN_SPLITS : splits);
+    const int rows_per_s = (S + splits - 1) / splits;
+    splits = (S + rows_per_s - 1) / rows_per_s;
+    gn_stats_rows_kernel<<<dim3(splits, B), 256, 0, st>>>(x, B, S, C, groups, cpg, tpr, rows_per_s, splits, partials);
+    TTB_CHECK_LAUNCH("gn_stats_rows_kernel");
+    const int rows_per_a = 16 * rows_par;     // two batches of 8 loads per thread; amortises the per-block stats fold
+    gn_apply_rows_kernel<<<dim3((S + rows_per_a - 1) / rows_per_a, B), 256, 0, st>>>(
+        x, S, C, groups, cpg, tpr, rows_per_a, splits, partials, gamma, beta, scale_shift, ss_bstride, ss_row, ss_row_stride,
+        do_silu, reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo, out_f32, ldof);
+    TTB_CHECK_LAUNCH("gn_apply_rows_kernel");
+    return 0;
+  }
+  const int splits = 8;      // generic (group-wise) path: any C % 4 == 0
   dim3 g1(groups, splits, B);
+  partials += 16;            // keep clear of the row-wise path's ticket at the head of the scratch buffer
   gn_stats_kernel<<<g1, 256, 0, st>>>(x, S, C, cpg, splits, partials);
   TTB_CHECK_LAUNCH("gn_stats_kernel");
   const long long total = (long long)S * (C >> 2);

@@ -5,7 +5,7 @@
 #include <cuda.h>
 #include <cstdlib>
 
-#define TTB_GN_SPLITS 8
+#define TTB_GN_SPLITS TTB_GROUPNORM_SPLITS   // row blocks of the GroupNorm statistics pass (include/ttb.h)
 
 namespace ttb {
 // flash_attn.cu: tcgen05 attention for the large shapes

@@ -194,7 +194,7 @@ class DiffusionEngine:
                     h=torch.empty(B, S, C, dtype=torch.float32, device=dev),
                     qkv=torch.empty(B, S, 3 * C, dtype=torch.bfloat16, device=dev),
                     o=torch.empty(B, S, C, dtype=torch.bfloat16, device=dev),
-                    partials=torch.empty(B * self.groups * 8 * 2, dtype=torch.float32, device=dev))
+                    partials=lib.groupnorm_scratch(B, self.groups, dev))
 
     # ------------------------------------------------------------------ timestep-independent conditioning
     def timestep_independent(self, latents, cond_latent, S):

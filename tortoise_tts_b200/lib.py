@@ -150,6 +150,11 @@ def rmsnorm(x, M, D, g, out_bf16):
     _chk(load().ttb_rmsnorm(_p(_f32(x)), M, D, _p(g), _p(_bf(out_bf16)), _stream()), "ttb_rmsnorm")
 
 
+def groupnorm_scratch(B, groups, device):
+    """Zeroed scratch for ttb_groupnorm (TTB_GROUPNORM_SCRATCH_FLOATS in include/ttb.h)."""
+    return torch.zeros(B * groups * (2 * 128 + 2) + 16, dtype=torch.float32, device=device)
+
+
 def groupnorm(x, B, S, Cc, groups, gamma, beta, partials, scale_shift=None, ss_bstride=0, ss_row=None, ss_row_stride=0,
               silu=False, out_bf16=None, ldo=0, out_f32=None, ldof=0):
     _chk(load().ttb_groupnorm(_p(_f32(x)), B, S, Cc, groups, _p(gamma), _p(beta), _p(scale_shift), ss_bstride,
