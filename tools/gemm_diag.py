@@ -73,8 +73,13 @@ def main():
         ("diff qkv", 1872, 3072, 1024, 1, 2, False, "bf16"),
         ("clvp qkv", 27520, 2304, 768, 1, 1, False, "bf16"),
         ("ar qkv", 256, 3072, 1024, 1, 1, False, "bf16"),
+        ("ar fc", 256, 4096, 1024, 1, 1, False, "bf16"),
+        ("ar proj", 256, 1024, 1024, 1, 1, False, "bf16"),
     ]
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
     for name, M, N, K, taps, batch, res, out in shapes:
+        if only and not name.startswith(only):
+            continue
         A = torch.randn(batch, M, K, device=dev).to(torch.bfloat16)
         W = (torch.randn(N, taps * K, device=dev) * 0.02).to(torch.bfloat16)
         bias = torch.zeros(N, device=dev)
@@ -94,6 +99,11 @@ def main():
             for v, nm in ((3, "5 stages"), (4, "4 stages")):
                 t1 = per_launch_us(lambda: lib.gemm(A, W, bias=bias, out_bf16=ob, tile_n=32, variant=v, **kw))
                 print("   tile  32 one-tile %s: %.1f us" % (nm, t1))
+            for v, nm in ((3, "8 stages, 1 CTA/SM"), (1, "4 stages")):
+                t1 = per_launch_us(lambda: lib.gemm(A, W, bias=bias, out_bf16=ob, tile_n=64, variant=v, **kw))
+                print("   tile  64 one-tile %s: %.1f us" % (nm, t1))
+                trace(lib, lambda: lib.gemm(A, W, bias=bias, out_bf16=ob, tile_n=64, variant=v, **kw),
+                      ((N + 63) // 64) * ((M + 127) // 128) * batch, "%s tile 64 %s" % (name, nm))
         for tile in tiles:
             for variant in (1, 2):
                 full = lambda: lib.gemm(A, W, bias=bias, residual=of if res else None, out_f32=of, out_bf16=ob,

@@ -53,5 +53,33 @@ def main():
               (impl, warm, nbytes / warm / 1e3, ts[len(ts) // 2], nbytes / ts[len(ts) // 2] / 1e3))
 
 
+def ln_main():
+    """residual + split-K-reduce + LayerNorm of the GPT-2 decode step (256 rows x 1024): warp-per-row vs block-per-row."""
+    from tortoise_tts_b200 import lib
+    dev = "cuda"
+    M, D, ns = 256, 1024, 4
+    x = torch.randn(M, D, device=dev)
+    part = torch.randn(ns, M, D, device=dev) * 0.1
+    bias, g1, b1 = torch.randn(D, device=dev), torch.randn(D, device=dev), torch.randn(D, device=dev)
+    ob = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    outs = {}
+    for impl in ("warp", "block"):
+        os.environ["TTB_LN_IMPL"] = impl
+        xx = x.clone()
+        lib.residual_layernorm(xx, M, D, part, ns, M * D, bias, g1, b1, out_bf16=ob)
+        torch.cuda.synchronize()
+        outs[impl] = (xx.clone(), ob.float().clone())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(100):
+            lib.residual_layernorm(xx, M, D, part, ns, M * D, bias, g1, b1, out_bf16=ob)
+        e1.record()
+        torch.cuda.synchronize()
+        print("residual_layernorm %-5s back-to-back %.2f us" % (impl, e0.elapsed_time(e1) / 100 * 1e3))
+    print("warp vs block: max |dx| %.2e, max |dy| %.2e" % ((outs["warp"][0] - outs["block"][0]).abs().max().item(),
+                                                           (outs["warp"][1] - outs["block"][1]).abs().max().item()))
+
+
 if __name__ == "__main__":
     main()
+    ln_main()

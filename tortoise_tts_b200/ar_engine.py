@@ -56,6 +56,8 @@ class AREngine:
 
     import os as _os
     DECODE_CLUSTER = int(_os.environ.get("TTB_AR_CLUSTER", "0"))
+    # TTB_AR_WIDE=1: c_attn / c_fc (N = 3D, 4D: one wave of 64-wide tiles) use 64-column tiles with an 8-stage pipeline
+    DECODE_WIDE = int(_os.environ.get("TTB_AR_WIDE", "0"))
     SPLITK_PROJ = 2     # attn.c_proj  (K = D):   32 n-tiles x 2 m-tiles x 2 splits = 128 CTAs at D=1024, B=256
     SPLITK_PROJ2 = 4    # mlp.c_proj   (K = 4D):  32 x 2 x 4 = 256 CTAs
 
@@ -160,20 +162,21 @@ class AREngine:
         s1 = min(self.SPLITK_PROJ, kb)
         s2 = min(self.SPLITK_PROJ2, 4 * kb)
         pa, pb = st["part_a"], st["part_b"]
+        wide = dict(tile_n=64, variant=3) if (self.DECODE_WIDE and not cl) else dict(tile_n=32)
         prev = None   # (partials, nsplit, bias) of the previous layer's mlp.c_proj, folded into the next LayerNorm
         for l, lw in enumerate(self.w.layers):
             if prev is None:
                 lib.layernorm(x, B, D, lw["ln1_g"], lw["ln1_b"], out_bf16=ws["a"])
             else:
                 lib.residual_layernorm(x, B, D, prev[0], prev[1], B * D, prev[2], lw["ln1_g"], lw["ln1_b"], out_bf16=ws["a"])
-            lib.gemm(ws["a"], lw["wqkv"], M=B, N=3 * D, K=D, bias=lw["bqkv"], out_bf16=ws["qkv"], tile_n=32, cluster=cl)
+            lib.gemm(ws["a"], lw["wqkv"], M=B, N=3 * D, K=D, bias=lw["bqkv"], out_bf16=ws["qkv"], cluster=cl, **wide)
             lib.ar_decode_attention(ws["qkv"], st["pk"][l], st["pv"][l], st["ck"][l], st["cv"][l], st["state"], B, H, P,
                                     Nmax, ws["o"], st["att_o"], st["att_lse"])
             lib.gemm(ws["o"], lw["wproj"], M=B, N=D, K=D, out_f32=pa, outf_bstride=B * D, tile_n=32, splitk=max(s1, 2), cluster=cl)
             lib.residual_layernorm(x, B, D, pa, self._nsplit(kb, max(s1, 2)), B * D, lw["bproj"], lw["ln2_g"], lw["ln2_b"],
                                    out_bf16=ws["a"])
             lib.gemm(ws["a"], lw["wfc"], M=B, N=4 * D, K=D, bias=lw["bfc"], act=lib.ACT_GELU_NEW, out_bf16=ws["h"],
-                     tile_n=32, cluster=cl)
+                     cluster=cl, **wide)
             lib.gemm(ws["h"], lw["wproj2"], M=B, N=D, K=4 * D, out_f32=pb, outf_bstride=B * D, tile_n=32, cluster=cl,
                      splitk=max(s2, 2))
             prev = (pb, self._nsplit(4 * kb, max(s2, 2)), lw["bproj2"])

@@ -426,6 +426,9 @@ extern "C" int ttb_gemm(const TtbGemmArgs* gp, void* stream) {
     if (t32 < 0) { const char* e = getenv("TTB_GEMM_T32_STAGES"); t32 = e ? atoi(e) : 5; }
     return (g.variant == 3 || (g.variant != 4 && t32 == 5)) ? launch_tc<32, 5>(g, ep, st) : launch_tc<32, 4>(g, ep, st);
   }
+  // 64-wide tiles, 8 stages, one CTA per SM (variant 3): for skinny problems whose 64-wide grid fits one wave, the deep
+  // pipeline keeps ~190 KB in flight per SM, which is what saturates an SM's inbound path (measured ~150-190 GB/s)
+  if (g.tile_n == 64 && g.variant == 3) return launch_tc<64, 8>(g, ep, st);
   if (g.tile_n == 64 || (g.tile_n == 0 && tiles128 < 148)) return launch_tc<64, 4>(g, ep, st);
   // large problems are L2-bandwidth bound with 128x128 tiles (64 flop/B at ~6.3 KB/clk of L2): 128x256 tiles raise the
   // intensity to 85 flop/B when the grid still covers most SMs

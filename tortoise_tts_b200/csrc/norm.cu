@@ -72,6 +72,78 @@ layernorm_kernel(const float* x, int D, const float* __restrict__ g1, const floa
   }
 }
 
+// One WARP per row (D = 128 * NV, NV <= 8): the row lives in NV float4 per lane, both statistics are xor-shuffle trees,
+// no shared memory and no block barrier. The GPT-2 decode step runs 61 of these on 256 rows between skinny GEMMs
+// (profiles/ncu_launches_r01_ar_decode_step.txt: 11.5 % of the step with the block-per-row kernel above, whose two
+// block_sum round trips dominate a 4 KB row). Same arithmetic as layernorm_kernel (two-pass variance, fixed
+// summation order of the split-K partials), only the reduction tree differs.
+
+template <int NV>
+__global__ void __launch_bounds__(64)
+layernorm_warp_kernel(const float* x, int M, int D, const float* __restrict__ g1, const float* __restrict__ b1,
+                      const float* __restrict__ g2, const float* __restrict__ b2, __nv_bfloat16* __restrict__ ob,
+                      float* __restrict__ of, float* xw, const float* __restrict__ partials, int nsplit,
+                      long long split_stride, const float* __restrict__ rbias) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 2 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float* xr = x + row * D;
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+  if (xw) {                     // fused residual update: x += bias + sum of split-K partials (fixed order)
+    float4 t[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      t[i] = rbias ? *reinterpret_cast<const float4*>(rbias + (i * 32 + lane) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sp = 0; sp < nsplit; ++sp) {
+      const float* pr = partials + sp * split_stride + row * D;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 p = *reinterpret_cast<const float4*>(pr + (i * 32 + lane) * 4);
+        t[i].x += p.x; t[i].y += p.y; t[i].z += p.z; t[i].w += p.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i].x += t[i].x; v[i].y += t[i].y; v[i].z += t[i].z; v[i].w += t[i].w;
+      *reinterpret_cast<float4*>(xw + row * D + (i * 32 + lane) * 4) = v[i];
+    }
+  }
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const float* gg = pass == 0 ? g1 : g2;
+    const float* bb = pass == 0 ? b1 : b2;
+    if (!gg) break;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) / D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / D + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 ga = *reinterpret_cast<const float4*>(gg + (i * 32 + lane) * 4);
+      const float4 be = *reinterpret_cast<const float4*>(bb + (i * 32 + lane) * 4);
+      v[i].x = (v[i].x - mean) * rstd * ga.x + be.x;
+      v[i].y = (v[i].y - mean) * rstd * ga.y + be.y;
+      v[i].z = (v[i].z - mean) * rstd * ga.z + be.z;
+      v[i].w = (v[i].w - mean) * rstd * ga.w + be.w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (ob) *reinterpret_cast<uint2*>(ob + row * D + c) = make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+    if (of) *reinterpret_cast<float4*>(of + row * D + c) = v[i];
+  }
+}
+
 template <int MAXV>
 __global__ void __launch_bounds__(256)
 rmsnorm_kernel(const float* __restrict__ x, int D, const float* __restrict__ g, __nv_bfloat16* __restrict__ ob) {
@@ -294,12 +366,35 @@ gn_apply_rows_kernel(const float* __restrict__ x, int S, int C, int groups, int 
 }  // namespace ttb
 using namespace ttb;
 
+// warp-per-row LayerNorm when the row is NV x 128 floats and everything is 16-byte aligned; false = not applicable
+static bool launch_ln_warp(const float* x, int M, int D, const float* g1, const float* b1, const float* g2, const float* b2,
+                           __nv_bfloat16* ob, float* of, float* xw, const float* partials, int nsplit,
+                           long long split_stride, const float* rbias, cudaStream_t st) {
+  const char* impl = getenv("TTB_LN_IMPL");          // "block" forces the block-per-row kernel (A/B timing)
+  if (impl && impl[0] == 'b') return false;
+  if (D % 128 != 0 || D > 1024 || (split_stride & 3)) return false;
+  const void* ptrs[] = {x, g1, b1, g2, b2, ob, of, xw, partials, rbias};
+  for (const void* p : ptrs)
+    if (p && (reinterpret_cast<uintptr_t>(p) & 15)) return false;
+  const dim3 grid((M + 1) / 2);
+#define TTB_LN_CASE(NV)                                                                                              \
+  case NV: layernorm_warp_kernel<NV><<<grid, 64, 0, st>>>(x, M, D, g1, b1, g2, b2, ob, of, xw, partials, nsplit,     \
+                                                          split_stride, rbias); break;
+  switch (D / 128) {
+    TTB_LN_CASE(1) TTB_LN_CASE(2) TTB_LN_CASE(3) TTB_LN_CASE(4) TTB_LN_CASE(5) TTB_LN_CASE(6) TTB_LN_CASE(7) TTB_LN_CASE(8)
+    default: return false;
+  }
+#undef TTB_LN_CASE
+  return true;
+}
+
 extern "C" int ttb_layernorm(const float* x, int M, int D, const float* g1, const float* b1, const float* g2,
                              const float* b2, void* out_bf16, float* out_f32, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (M <= 0) return 0;
   auto ob = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-  if (D <= 1024) layernorm_kernel<4><<<M, 256, 0, st>>>(x, D, g1, b1, g2, b2, ob, out_f32, nullptr, nullptr, 0, 0, nullptr);
+  if (launch_ln_warp(x, M, D, g1, b1, g2, b2, ob, out_f32, nullptr, nullptr, 0, 0, nullptr, st)) {}
+  else if (D <= 1024) layernorm_kernel<4><<<M, 256, 0, st>>>(x, D, g1, b1, g2, b2, ob, out_f32, nullptr, nullptr, 0, 0, nullptr);
   else if (D <= 4096) layernorm_kernel<16><<<M, 256, 0, st>>>(x, D, g1, b1, g2, b2, ob, out_f32, nullptr, nullptr, 0, 0, nullptr);
   else { set_error("ttb_layernorm: D=%d > 4096", D); return -1; }
   TTB_CHECK_LAUNCH("layernorm_kernel");
@@ -312,7 +407,8 @@ extern "C" int ttb_residual_layernorm(float* x, int M, int D, const float* parti
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (M <= 0) return 0;
   auto ob = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-  if (D <= 1024) layernorm_kernel<4><<<M, 256, 0, st>>>(x, D, g1, b1, g2, b2, ob, out_f32, x, partials, nsplit, split_stride, bias);
+  if (launch_ln_warp(x, M, D, g1, b1, g2, b2, ob, out_f32, x, partials, nsplit, split_stride, bias, st)) {}
+  else if (D <= 1024) layernorm_kernel<4><<<M, 256, 0, st>>>(x, D, g1, b1, g2, b2, ob, out_f32, x, partials, nsplit, split_stride, bias);
   else if (D <= 4096) layernorm_kernel<16><<<M, 256, 0, st>>>(x, D, g1, b1, g2, b2, ob, out_f32, x, partials, nsplit, split_stride, bias);
   else { set_error("ttb_residual_layernorm: D=%d > 4096", D); return -1; }
   TTB_CHECK_LAUNCH("layernorm_kernel(residual)");
