@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda.h>
 #include <stdint.h>
+#include <cstdlib>
 
 #define TTB_DEVINL __device__ __forceinline__
 
@@ -18,6 +19,45 @@ int check_cuda(cudaError_t e, const char* what);
     cudaError_t _e = cudaGetLastError();                         \
     if (_e != cudaSuccess) return ttb::check_cuda(_e, what);     \
   } while (0)
+
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// Every kernel of the two per-step CUDA graphs starts with pdl_launch_dependents() and calls pdl_wait() before its
+// first access to global memory that an earlier kernel may have written (and before its own first global write).
+// Launched the ordinary way both instructions are no-ops. With TTB_PDL=1 the host launches these kernels with
+// cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs are scheduled, run their prologue
+// (barrier init, TMEM allocation, descriptor prefetch) and park in griddepcontrol.wait while the previous kernel
+// drains, which removes the kernel-to-kernel launch gap that dominates the ~10 us decode-step kernels.
+// Off by default in round 1: not yet validated on hardware.
+TTB_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+TTB_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TTB_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// kernel<<<grid, block, smem, st>>>(args...) with the PDL launch attribute when TTB_PDL=1. Only for kernels that
+// contain pdl_wait().
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  if (pdl_enabled()) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ------------------------------------------------------------------ small math
 TTB_DEVINL float silu(float x) { return x / (1.0f + __expf(-x)); }

@@ -127,6 +127,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   // optional per-CTA phase timestamps (ttb_debug_gemm_trace): 8 x u64 per CTA, see tools/gemm_diag.py
   unsigned long long* tr = trace ? trace + 8ull * (blockIdx.x + gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z)) : nullptr;
   if (tr && threadIdx.x == 0) { tr[0] = global_timer_ns(); tr[1] = sm_id(); }
+  pdl_launch_dependents();
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* accum_bar = empty_bar + STAGES;
@@ -155,6 +156,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                    // operands, residual and outputs belong to earlier kernels until here
   if (tr && threadIdx.x == 0) tr[2] = global_timer_ns();
 
   if (warp == 0) {
@@ -292,9 +294,9 @@ static int launch_tc(const TtbGemmArgs& g, const GemmEpilogue& ep, cudaStream_t 
     zdim = (kb_total + kb_per_split - 1) / kb_per_split;     // every split owns >= 1 k-block
   }
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, zdim);
-  gemm_bf16_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, st>>>(ma, mb, g.M, g.N, g.K, g.taps, g.pad,
-                                                                        (bcast || g.splitk > 1) ? 0 : 1, kb_per_split, ep,
-                                                                        g_gemm_trace);
+  cudaError_t le = launch_pdl(gemm_bf16_tc_kernel<BN, STAGES>, grid, dim3(GEMM_THREADS), (size_t)L::TOTAL, st, ma, mb, g.M, g.N,
+                              g.K, g.taps, g.pad, (bcast || g.splitk > 1) ? 0 : 1, kb_per_split, ep, g_gemm_trace);
+  if (le != cudaSuccess) return check_cuda(le, "gemm_bf16_tc_kernel launch");
   TTB_CHECK_LAUNCH("gemm_bf16_tc_kernel");
   return 0;
 }

@@ -38,6 +38,7 @@ gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const 
   uint64_t* acc_empty = acc_full + 2;           // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int kblocks_per_tap = K / BK;
@@ -56,6 +57,7 @@ gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
