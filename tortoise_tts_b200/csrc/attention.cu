@@ -157,6 +157,8 @@ ar_decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16
                       const __nv_bfloat16* __restrict__ pv, __nv_bfloat16* __restrict__ ck,
                       __nv_bfloat16* __restrict__ cv, const TtbArState* __restrict__ state, int B, int H, int P, int Nmax,
                       float* __restrict__ o_c, float* __restrict__ lse_c) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int h = blockIdx.x;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y * DEC_WARPS + w;
@@ -269,6 +271,8 @@ ar_decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16
 __global__ void ar_attn_merge_kernel(const float* __restrict__ o_p, const float* __restrict__ lse_p,
                                      const float* __restrict__ o_c, const float* __restrict__ lse_c, int B, int H,
                                      __nv_bfloat16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over B * H * 16 (4 dims each)
   if (i >= (long long)B * H * 16) return;
   const long long bh = i >> 4;
@@ -346,18 +350,20 @@ extern "C" int ttb_ar_decode_attention(const void* qkv, const void* prefix_k, co
   a.out_f32 = o_p; a.lse = lse_p;
   if (flash_attention_launch(a, g_fj.side)) return -1;
   dim3 grid(H, (B + DEC_WARPS - 1) / DEC_WARPS);
-  ar_decode_attn_kernel<<<grid, DEC_THREADS, 0, st>>>(
+  const cudaError_t le1 = launch_pdl(ar_decode_attn_kernel, grid, dim3(DEC_THREADS), (size_t)0, st,
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(prefix_k),
       reinterpret_cast<const __nv_bfloat16*>(prefix_v), reinterpret_cast<__nv_bfloat16*>(cand_k),
       reinterpret_cast<__nv_bfloat16*>(cand_v), state, B, H, P, Nmax, o_c, lse_c);
+  if (le1 != cudaSuccess) return check_cuda(le1, "ar_decode_attn_kernel launch");
   TTB_CHECK_LAUNCH("ar_decode_attn_kernel");
   // join, then merge the two partials
   e = cudaEventRecord(g_fj.join, g_fj.side);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(st, g_fj.join, 0);
   if (e != cudaSuccess) return check_cuda(e, "decode attention join");
   const long long n = (long long)B * H * 16;
-  ar_attn_merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(o_p, lse_p, o_c, lse_c, B, H,
-                                                                   reinterpret_cast<__nv_bfloat16*>(out));
+  const cudaError_t le2 = launch_pdl(ar_attn_merge_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, st, o_p, lse_p,
+                                     o_c, lse_c, B, H, reinterpret_cast<__nv_bfloat16*>(out));
+  if (le2 != cudaSuccess) return check_cuda(le2, "ar_attn_merge_kernel launch");
   TTB_CHECK_LAUNCH("ar_attn_merge_kernel");
   return 0;
 }

@@ -27,7 +27,11 @@ int check_cuda(cudaError_t e, const char* what);
 // cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs are scheduled, run their prologue
 // (barrier init, TMEM allocation, descriptor prefetch) and park in griddepcontrol.wait while the previous kernel
 // drains, which removes the kernel-to-kernel launch gap that dominates the ~10 us decode-step kernels.
-// Off by default in round 1: not yet validated on hardware.
+// Measured in round 1 (profiles/bench_r01_pdl.txt): TTB_PDL=1 is correct (GPU parity tests pass, CUDA-graph capture of
+// the programmatic edges works) but SLOWER, AR 1346 -> 1445 ms: with the trigger at the very top of every kernel the
+// dependent's CTAs become resident at once and take registers / shared memory away from the kernel that is still
+// running (the decode-attention kernel loses occupancy). Hence off by default; next step is to move the trigger to each
+// kernel's tail (after its main loop) so that only launch latency and prologue overlap.
 TTB_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 TTB_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

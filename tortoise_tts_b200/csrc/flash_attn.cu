@@ -39,6 +39,8 @@ template <int MINB>
 __global__ void __launch_bounds__(FA_THREADS, MINB)
 flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                      const __grid_constant__ CUtensorMap map_v, TtbAttnArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FaSmem::BAR_OFF);
@@ -308,8 +310,9 @@ int flash_attention_launch(const TtbAttnArgs& a, cudaStream_t st) {
     if (r != cudaSuccess) { occ = 0; return check_cuda(r, "cudaFuncSetAttribute(flash_attn)"); }
   }
   dim3 grid((a.T + FA_BM - 1) / FA_BM, a.H, a.nseq);
-  if (occ == 3) flash_attn_tc_kernel<3><<<grid, FA_THREADS, FaSmem::TOTAL, st>>>(mq, mk, mv, a);
-  else flash_attn_tc_kernel<2><<<grid, FA_THREADS, FaSmem::TOTAL, st>>>(mq, mk, mv, a);
+  const cudaError_t le = (occ == 3) ? launch_pdl(flash_attn_tc_kernel<3>, grid, dim3(FA_THREADS), (size_t)FaSmem::TOTAL, st, mq, mk, mv, a)
+                                    : launch_pdl(flash_attn_tc_kernel<2>, grid, dim3(FA_THREADS), (size_t)FaSmem::TOTAL, st, mq, mk, mv, a);
+  if (le != cudaSuccess) return check_cuda(le, "flash_attn_tc_kernel launch");
   TTB_CHECK_LAUNCH("flash_attn_tc_kernel");
   return 0;
 }

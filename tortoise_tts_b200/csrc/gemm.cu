@@ -345,8 +345,9 @@ static int launch_persistent(const TtbGemmArgs& g, const GemmEpilogue& ep, cudaS
   const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
   const long long total = (long long)m_tiles * n_tiles * zdim;
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  gemm_bf16_tc_persistent_kernel<BN, PSTAGES, EW><<<grid, 64 + 32 * EW, L::TOTAL, st>>>(
+  const cudaError_t le = launch_pdl(gemm_bf16_tc_persistent_kernel<BN, PSTAGES, EW>, dim3(grid), dim3(64 + 32 * EW), (size_t)L::TOTAL, st,
       ma, mb, g.M, g.N, g.K, g.taps, g.pad, (bcast || g.splitk > 1) ? 0 : 1, kb_per_split, m_tiles, n_tiles, zdim, ep);
+  if (le != cudaSuccess) return check_cuda(le, "gemm_bf16_tc_persistent_kernel launch");
   TTB_CHECK_LAUNCH("gemm_bf16_tc_persistent_kernel");
   return 0;
 }

@@ -84,6 +84,8 @@ layernorm_warp_kernel(const float* x, int M, int D, const float* __restrict__ g1
                       const float* __restrict__ g2, const float* __restrict__ b2, __nv_bfloat16* __restrict__ ob,
                       float* __restrict__ of, float* xw, const float* __restrict__ partials, int nsplit,
                       long long split_stride, const float* __restrict__ rbias) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 2 + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -259,6 +261,8 @@ gn_apply_kernel(const float* __restrict__ x, int S, int C, int groups, int cpg, 
 __global__ void __launch_bounds__(256)
 gn_stats_rows_kernel(const float* __restrict__ x, int B, int S, int C, int groups, int cpg, int tpr, int rows_per,
                      int splits, float* __restrict__ scratch) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sacc[2 * 256];                               // [row lane][group][2]; rows_par * groups = 256 / lpg
   const int sp = blockIdx.x, b = blockIdx.y;
   const int rows_par = 256 / tpr;
@@ -308,6 +312,8 @@ gn_apply_rows_kernel(const float* __restrict__ x, int S, int C, int groups, int 
                      const float* __restrict__ scratch, const float* __restrict__ gamma, const float* __restrict__ beta,
                      const float* __restrict__ ss, int ss_bstride, const int* __restrict__ ss_row, int ss_row_stride,
                      int do_silu, __nv_bfloat16* __restrict__ ob, int ldo, float* __restrict__ of, int ldof) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   const int rows_par = 256 / tpr;
   const int rl = threadIdx.x / tpr, ct = threadIdx.x - rl * tpr;
@@ -378,8 +384,8 @@ static bool launch_ln_warp(const float* x, int M, int D, const float* g1, const 
     if (p && (reinterpret_cast<uintptr_t>(p) & 15)) return false;
   const dim3 grid((M + 1) / 2);
 #define TTB_LN_CASE(NV)                                                                                              \
-  case NV: layernorm_warp_kernel<NV><<<grid, 64, 0, st>>>(x, M, D, g1, b1, g2, b2, ob, of, xw, partials, nsplit,     \
-                                                          split_stride, rbias); break;
+  case NV: launch_pdl(layernorm_warp_kernel<NV>, grid, dim3(64), (size_t)0, st, x, M, D, g1, b1, g2, b2, ob, of, xw,  \
+                      partials, nsplit, split_stride, rbias); break;
   switch (D / 128) {
     TTB_LN_CASE(1) TTB_LN_CASE(2) TTB_LN_CASE(3) TTB_LN_CASE(4) TTB_LN_CASE(5) TTB_LN_CASE(6) TTB_LN_CASE(7) TTB_LN_CASE(8)
     default: return false;
@@ -443,11 +449,11 @@ extern "C" int ttb_groupnorm(const float* x, int B, int S, int C, int groups, co
     splits = splits < 1 ? 1 : (splits > TTB_GN_SPLITS ? TTB_GN_SPLITS : splits);
     const int rows_per_s = (S + splits - 1) / splits;
     splits = (S + rows_per_s - 1) / rows_per_s;
-    gn_stats_rows_kernel<<<dim3(splits, B), 256, 0, st>>>(x, B, S, C, groups, cpg, tpr, rows_per_s, splits, partials);
+    launch_pdl(gn_stats_rows_kernel, dim3(splits, B), dim3(256), (size_t)0, st, x, B, S, C, groups, cpg, tpr, rows_per_s, splits, partials);
     TTB_CHECK_LAUNCH("gn_stats_rows_kernel");
     const int rows_per_a = 16 * rows_par;     // two batches of 8 loads per thread; amortises the per-block stats fold
-    gn_apply_rows_kernel<<<dim3((S + rows_per_a - 1) / rows_per_a, B), 256, 0, st>>>(
-        x, S, C, groups, cpg, tpr, rows_per_a, splits, partials, gamma, beta, scale_shift, ss_bstride, ss_row, ss_row_stride,
+    launch_pdl(gn_apply_rows_kernel, dim3((S + rows_per_a - 1) / rows_per_a, B), dim3(256), (size_t)0, st,
+        x, S, C, groups, cpg, tpr, rows_per_a, splits, (const float*)partials, gamma, beta, scale_shift, ss_bstride, ss_row, ss_row_stride,
         do_silu, reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo, out_f32, ldof);
     TTB_CHECK_LAUNCH("gn_apply_rows_kernel");
     return 0;
