@@ -99,3 +99,58 @@ def _pair_worker(rank, ws, port, ret):
 def test_cfg_pair_split_world2():
     port = _free_port()
     mp.spawn(_pair_worker, args=(2, port, None), nprocs=2, join=True)
+
+
+def test_gather_and_broadcast_world4_ragged():
+    """13 candidates over 4 ranks (4, 4, 4, 1): the padded all-gather still returns the global order bit-exactly."""
+    port = _free_port()
+    mp.spawn(_worker, args=(4, port, 13, 9), nprocs=4, join=True)
+
+
+def _pair_worker4(rank, ws, port, ret):
+    """world 4, k = 1: the pair (0, 1) renders the only selected candidate, ranks 2 and 3 take no part in the denoiser
+    but must create the pair groups and join the final broadcast (the layout bench.py --gpus 4/8 runs)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import lib_emu
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        lib_emu.install()
+        from tortoise_tts_b200.config import ModelConfig
+        from tortoise_tts_b200.synth import synth_all
+        from tortoise_tts_b200.diffusion_engine import DiffusionEngine
+        cfg = ModelConfig.small()
+        sds = synth_all(cfg, seed=0, suppress_stop=False)
+        g = torch.Generator().manual_seed(5)
+        N, iters = 8, 2
+        S = N * 4 * 24000 // 22050
+        lat = torch.randn(N, cfg.ar_dim, generator=g)
+        cond = torch.randn(2 * cfg.diff_dim, generator=g) * 0.3
+        n0 = torch.randn(100, S, generator=g)
+        sn = torch.randn(iters, 100, S, generator=g)
+        groups, npairs = parallel.pair_groups()
+        assert npairs == 2
+        owner, p = parallel.render_plan(0, ws, True)
+        assert (owner, p) == (0, 0)
+        mel = None
+        if rank in (owner, owner + 1):
+            eng = DiffusionEngine(sds["diffusion"], cfg, device="cpu")
+            mel = eng.sample(lat, cond, iters, n0, sn, cond_free=True, cond_free_k=2.0, use_graph=False,
+                             pair=(groups[p], rank - owner))
+        n = torch.tensor([mel.numel() if rank == owner else 0], dtype=torch.int64)
+        dist.broadcast(n, src=owner)
+        got = parallel.broadcast_from_owner(mel.reshape(-1) if rank == owner else None, int(n.item()), owner,
+                                            torch.device("cpu"))
+        assert got.numel() == 100 * S and bool(torch.isfinite(got).all())
+        ref = DiffusionEngine(sds["diffusion"], cfg, device="cpu").sample(lat, cond, iters, n0, sn, cond_free=True,
+                                                                          cond_free_k=2.0, use_graph=False)
+        assert (got.reshape(100, S) - ref).abs().max().item() < 1e-4
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cfg_pair_split_world4():
+    port = _free_port()
+    mp.spawn(_pair_worker4, args=(4, port, None), nprocs=4, join=True)
