@@ -68,3 +68,25 @@ def test_synth_layout_param_counts():
     sds = synth_all(ModelConfig.small())
     assert "gpt.h.1.mlp.c_proj.weight" in sds["autoregressive"]
     assert sds["vocoder"]["res_stack.0.kernel_predictor.kernel_conv.weight_v"].shape == (24576, 64, 3)
+
+
+def test_cpu_baseline_thread_probe():
+    """bench.py's CPU arm must size its thread pool from what the process may use, never from os.cpu_count()."""
+    import os
+    from oracle import cpu_baseline as cb
+    n = cb.host_threads()
+    assert 1 <= n <= 64
+    if hasattr(os, "sched_getaffinity"):
+        assert n <= len(os.sched_getaffinity(0))
+    assert cb.host_threads(cap=2) <= 2
+
+
+def test_build_stamp_is_content_hash():
+    """The kernel library is rebuilt when a source changes, not when file times change (a copied tree keeps no times)."""
+    import os
+    from tortoise_tts_b200 import build as b
+    h1 = b._source_hash()
+    assert len(h1) == 64 and h1 == b._source_hash()
+    if os.path.exists(b.STAMP) and os.path.exists(b.LIB) and open(b.STAMP).read().strip() != h1:
+        import warnings
+        warnings.warn("libttb.so is older than csrc/: __graft_entry__.build() will recompile it")
