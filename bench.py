@@ -23,6 +23,12 @@ if ROOT not in sys.path:
 
 METRIC = "audio-seconds/sec at preset='standard'"
 UNIT = "audio-s/s"
+# ncu --set full, one launch each at the bench shapes (profiles/ncu_r01/*.ncu-rep): DRAM bytes read + written
+NCU_TRAFFIC_BYTES = {
+    "AR decode attention": 228.770560e6 + 8.168192e6,      # candidate KV stream kernel, ctx 174+215 (225.4 MB algorithmic)
+    "diffusion attention": 23.328768e6,                    # qkv 23.0 MB read once; output stays in L2
+    "diffusion conv k=3 GEMM": 29.341696e6 + 6.656e3,      # A 7.7 + W 6.3 + residual 15.3 MB; output stays in L2
+}
 
 
 def load_tokens(name="para53"):
@@ -247,8 +253,15 @@ def run_engine(args):
         probes, how = kernel_probes(tts, cfg, n_mel, B, len(tokens) + 5)
         progress("probes done")
         dom = max(probes, key=lambda d: d["total_ms_per_utterance"])
+        # dram__bytes_read + dram__bytes_write per launch of the dominant kernel from the committed ncu --set full
+        # captures (profiles/ncu_summary_r01_run10.txt, same shapes as the probes); null for a kernel without a capture
+        traffic = None
+        for key, val in NCU_TRAFFIC_BYTES.items():
+            if dom["kernel"].startswith(key):
+                traffic = val
         line["roofline"] = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": round(dom["achieved"], 2),
-                            "peak": dom["peak"], "unit": dom["unit"], "frac": round(dom["frac"], 4), "traffic": None,
+                            "peak": dom["peak"], "unit": dom["unit"], "frac": round(dom["frac"], 4), "traffic": traffic,
+                            "traffic_source": "profiles/ncu_summary_r01_run10.txt" if traffic else None,
                             "peak_source": how, "launch_ms": round(dom["ms"], 4)}
         line["kernels"] = [{k_: (round(v, 4) if isinstance(v, float) else v) for k_, v in d.items()} for d in probes]
         if not args.no_cpu_baseline:
