@@ -338,3 +338,23 @@ def test_tts_end_to_end_small(small):
         tts.tts_with_preset("x", preset="nope", **kw)
     with pytest.raises(AssertionError):
         tts.tts("x", text_tokens=[5] * 400, conditioning_latents=cl)
+
+
+@pytest.mark.gpu
+def test_tts_long_concatenates_chunks(small):
+    """≙ read.py:44-85: every chunk is synthesised with the same seed and latents; the result is the concatenation."""
+    from tortoise_tts_b200.api import TextToSpeech
+    cfg, sds, g = small
+    tts = TextToSpeech(state_dicts=sds, config=cfg, kv_cache=True)
+    cl = (torch.randn(1, cfg.ar_dim), torch.randn(1, 2 * cfg.diff_dim) * 0.3)
+    kw = dict(conditioning_latents=cl, use_deterministic_seed=5, max_mel_tokens=24, num_autoregressive_samples=8,
+              diffusion_iterations=4, verbose=False)
+    toks = [TEXT[:-1], TEXT[1:-1]]
+    whole = tts.tts_long("first chunk|second chunk", preset="ultra_fast", text_tokens_list=toks, **kw)
+    parts = [tts.tts_with_preset("unused", preset="ultra_fast", text_tokens=t, **kw) for t in toks]
+    assert whole.dim() == 2 and whole.shape[0] == 1
+    assert torch.equal(whole, torch.cat([p.reshape(1, -1) for p in parts], dim=-1))
+    with pytest.raises(NotImplementedError):
+        tts.tts_long("a|b", preset="ultra_fast", text_tokens_list=toks, k=2, **kw)
+    with pytest.raises(ValueError):
+        tts.tts_long("a|b|c", preset="ultra_fast", text_tokens_list=toks, **kw)

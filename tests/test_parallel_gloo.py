@@ -154,3 +154,28 @@ def _pair_worker4(rank, ws, port, ret):
 def test_cfg_pair_split_world4():
     port = _free_port()
     mp.spawn(_pair_worker4, args=(4, port, None), nprocs=4, join=True)
+
+
+def _utt_worker(rank, ws, port, n_utt):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        from tortoise_tts_b200.text import utterance_plan
+        plan = utterance_plan(n_utt, ws)
+        with parallel.single_rank():
+            assert parallel.world() == (0, 1)          # inside: the rank works alone, no collective is issued
+            parts = {u: torch.full((50 + 7 * u,), float(u + 1)) for u in range(n_utt) if plan[u] == rank}
+        assert parallel.world() == (rank, ws)
+        got = parallel.exchange_utterances(parts, plan, torch.device("cpu"))
+        assert len(got) == n_utt
+        for u, w in enumerate(got):
+            assert w.shape == (50 + 7 * u,) and bool((w == u + 1).all())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_utterance_sharding_world3():
+    """Long-form mode: utterance u on rank u % G, ragged lengths, every rank gets all of them."""
+    port = _free_port()
+    mp.spawn(_utt_worker, args=(3, port, 7), nprocs=3, join=True)

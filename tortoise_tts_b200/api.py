@@ -120,6 +120,42 @@ class TextToSpeech:
         settings.update(kwargs)
         return self.tts(text, **settings)
 
+    def tts_long(self, text, preset="standard", shard_utterances=True, text_tokens_list=None, **kwargs):
+        """≙ the loop of the reference's `read.py:44-85` for one voice: split the text (`'|'` forces the split points,
+        else `split_and_recombine_text`), synthesise every chunk with the SAME seed and conditioning latents, and
+        concatenate the waveforms (k = 1). Returns `[1, samples]` on the CPU.
+
+        With several ranks and `shard_utterances`, chunk u is rendered WHOLE by rank u % G (no
+        collective inside an utterance, so the per-step latency floor of the candidate-sharded mode does not apply)
+        and the waveforms are exchanged once at the end. `text_tokens_list` (one id list per chunk) bypasses the
+        tokenizer, as `text_tokens` does for `tts()`."""
+        from .text import split_and_recombine_text, utterance_plan
+        if kwargs.get("k", 1) != 1:
+            raise NotImplementedError("tts_long concatenates one waveform per chunk (read.py:77-79): k must be 1")
+        texts = text.split("|") if "|" in text else split_and_recombine_text(text)      # read.py:46-52
+        if text_tokens_list is not None and len(text_tokens_list) != len(texts):
+            raise ValueError("text_tokens_list has %d entries for %d chunks" % (len(text_tokens_list), len(texts)))
+        rank, ws = parallel.world()
+        spread = bool(shard_utterances) and ws > 1
+        plan = utterance_plan(len(texts), ws if spread else 1)
+        parts = {}
+        for u, chunk in enumerate(texts):
+            kw = dict(kwargs)
+            if text_tokens_list is not None:
+                kw["text_tokens"] = text_tokens_list[u]
+            if spread:
+                if plan[u] != rank:
+                    continue
+                with parallel.single_rank():
+                    parts[u] = self.tts_with_preset(chunk, preset=preset, **kw).reshape(-1)
+            else:
+                parts[u] = self.tts_with_preset(chunk, preset=preset, **kw).reshape(-1)
+        if spread:
+            wavs = parallel.exchange_utterances(parts, plan, self.device)
+        else:
+            wavs = [parts[u] for u in range(len(texts))]
+        return torch.cat([w.reshape(1, -1).cpu() for w in wavs], dim=-1)
+
     def tts(self, text, voice_samples=None, conditioning_latents=None, k=1, verbose=True, use_deterministic_seed=None,
             return_deterministic_state=False, num_autoregressive_samples=512, temperature=.8, length_penalty=1,
             repetition_penalty=2.0, top_p=.8, max_mel_tokens=500, cvvp_amount=.0, diffusion_iterations=100,

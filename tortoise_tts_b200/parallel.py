@@ -10,10 +10,28 @@ import torch
 import torch.distributed as dist
 
 
+_SINGLE = 0   # > 0 inside single_rank(): this rank works alone (utterance-level sharding)
+
+
 def world():
-    if dist.is_available() and dist.is_initialized():
+    if _SINGLE == 0 and dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
+
+
+class single_rank:
+    """Context in which `world()` reports one rank: the calls inside do all their work locally and issue no collective.
+    Used when whole utterances, not candidates, are spread over the GPUs."""
+
+    def __enter__(self):
+        global _SINGLE
+        _SINGLE += 1
+        return self
+
+    def __exit__(self, *exc):
+        global _SINGLE
+        _SINGLE -= 1
+        return False
 
 
 def shard_range(total, rank, world_size):
@@ -80,3 +98,19 @@ def broadcast_from_owner(t, numel, owner, device, dtype=torch.float32):
     buf = t.contiguous() if rank == owner else torch.empty(numel, dtype=dtype, device=device)
     dist.broadcast(buf, src=owner)
     return buf
+
+
+def exchange_utterances(parts, plan, device, dtype=torch.float32):
+    """`parts[u]` = 1-D waveform of utterance u on its owner `plan[u]` (absent elsewhere). Returns the list of all
+    utterances on every rank: per utterance one length broadcast and one payload broadcast from its owner."""
+    rank, ws = world()
+    out = []
+    for u, owner in enumerate(plan):
+        if ws == 1:
+            out.append(parts[u])
+            continue
+        mine = parts[u].to(device=device, dtype=dtype).reshape(-1) if owner == rank else None
+        n = torch.tensor([mine.numel() if owner == rank else 0], dtype=torch.int64, device=device)
+        dist.broadcast(n, src=owner)
+        out.append(broadcast_from_owner(mine, int(n.item()), owner, device, dtype))
+    return out
