@@ -48,7 +48,9 @@ typedef struct TtbGemmArgs {
   int cluster;          /* 2 or 4: CTAs adjacent in N form a cluster and share the activation tile by TMA multicast
                            (tile_n picks the tile width: 32, 64, else 128); 0/1 = off */
   int variant;          /* 0 = auto; 1 = one tile per CTA; 2 = persistent kernel; with tile_n = 32 also 3 / 4 = one tile
-                           per CTA with a 5- / 4-stage pipeline (tools/gemm_sweep.py, tools/gemm_diag.py) */
+                           per CTA with a 5- / 4-stage pipeline (tools/gemm_sweep.py, tools/gemm_diag.py).
+                           Experiments not yet validated on hardware (never chosen automatically): 5 = two TMA issuer
+                           threads per CTA, 6 = CTA-pair kernel (tcgen05 cta_group::2, 256 x tile_n tiles, tile_n 128 / 256) */
 } TtbGemmArgs;
 
 /* nn.Linear / HF Conv1D / nn.Conv1d(k=1,3) as one tcgen05 GEMM with fused bias/activation/residual.

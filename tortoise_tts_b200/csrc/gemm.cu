@@ -116,7 +116,10 @@ struct GemmSmem {
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
 };
 
-template <int BN, int STAGES>
+// SPLIT_PRODUCER (experiment, variant 5): the A tiles are issued by warp 0 and the B tiles by lane 0 of the first epilogue
+// warp (idle during the mainloop). Measured in round 1: one CTA receives its operands at ~46 B/clk whatever the stage
+// count or tile width, two co-resident CTAs at twice that; if the limit is per issuing thread, two issuers double it.
+template <int BN, int STAGES, bool SPLIT_PRODUCER = false>
 __global__ void __launch_bounds__(GEMM_THREADS, BN <= 128 ? 2 : 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
                     int K, int taps, int pad, int a_batch_mul, int kb_per_split, GemmEpilogue ep,
@@ -147,7 +150,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], SPLIT_PRODUCER ? 2 : 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(accum_bar, 1);
     fence_barrier_init();
   }
@@ -170,9 +173,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int kk = (kb - tap * kblocks_per_tap) * BK;
         uint8_t* sa = smem + stage * L::STAGE_BYTES;
         uint8_t* sb = sa + L::A_BYTES;
-        mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-        tma_load_3d(sa, &map_a, &full_bar[stage], kk, m0 + tap - pad, bz * a_batch_mul);
-        tma_load_3d(sb, &map_b, &full_bar[stage], tap * K + kk, n0, 0);
+        if constexpr (SPLIT_PRODUCER) {
+          mbar_arrive_expect_tx(&full_bar[stage], L::A_BYTES);
+          tma_load_3d(sa, &map_a, &full_bar[stage], kk, m0 + tap - pad, bz * a_batch_mul);
+        } else {
+          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          tma_load_3d(sa, &map_a, &full_bar[stage], kk, m0 + tap - pad, bz * a_batch_mul);
+          tma_load_3d(sb, &map_b, &full_bar[stage], tap * K + kk, n0, 0);
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -202,6 +210,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   } else {
     // ===== epilogue: warps 2..5; warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
     const int q = warp & 3;
+    if constexpr (SPLIT_PRODUCER) {
+      if (warp == 2 && lane == 0) {                 // second TMA issuer: the weight tiles
+        int stage = 0; uint32_t phase = 0;
+        for (int kbi = 0; kbi < num_kb; ++kbi) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const int kb = kb_begin + kbi;
+          const int tap = kb / kblocks_per_tap;
+          const int kk = (kb - tap * kblocks_per_tap) * BK;
+          uint8_t* sb = smem + stage * L::STAGE_BYTES + L::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], L::B_BYTES);
+          tma_load_3d(sb, &map_b, &full_bar[stage], tap * K + kk, n0, 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      __syncwarp();
+    }
     if (ep.residual) {
       // these warps idle during the mainloop: pull the tile's residual rows into L2 meanwhile
       const int m = m0 + q * 32 + lane;
@@ -270,7 +294,7 @@ __global__ void gemm_ref_kernel(const __nv_bfloat16* A, long long a_bstride, int
 static int g_gemm_impl = -1;  // 0 = tcgen05, 1 = SIMT reference (bring-up only; TTB_GEMM_IMPL=ref)
 static unsigned long long* g_gemm_trace = nullptr;   // ttb_debug_gemm_trace
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool SPLIT_PRODUCER = false>
 static int launch_tc(const TtbGemmArgs& g, const GemmEpilogue& ep, cudaStream_t st) {
   CUtensorMap ma, mb;
   // a_bstride == 0 broadcasts one activation tensor to every batch item (batch dim of extent 1, coordinate 0)
@@ -283,7 +307,7 @@ static int launch_tc(const TtbGemmArgs& g, const GemmEpilogue& ep, cudaStream_t 
   using L = GemmSmem<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, STAGES, SPLIT_PRODUCER>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm)");
     attr_set = true;
   }
@@ -294,7 +318,7 @@ static int launch_tc(const TtbGemmArgs& g, const GemmEpilogue& ep, cudaStream_t 
     zdim = (kb_total + kb_per_split - 1) / kb_per_split;     // every split owns >= 1 k-block
   }
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, zdim);
-  cudaError_t le = launch_pdl(gemm_bf16_tc_kernel<BN, STAGES>, grid, dim3(GEMM_THREADS), (size_t)L::TOTAL, st, ma, mb, g.M, g.N,
+  cudaError_t le = launch_pdl(gemm_bf16_tc_kernel<BN, STAGES, SPLIT_PRODUCER>, grid, dim3(GEMM_THREADS), (size_t)L::TOTAL, st, ma, mb, g.M, g.N,
                               g.K, g.taps, g.pad, (bcast || g.splitk > 1) ? 0 : 1, kb_per_split, ep, g_gemm_trace);
   if (le != cudaSuccess) return check_cuda(le, "gemm_bf16_tc_kernel launch");
   TTB_CHECK_LAUNCH("gemm_bf16_tc_kernel");
@@ -305,6 +329,7 @@ static int launch_tc(const TtbGemmArgs& g, const GemmEpilogue& ep, cudaStream_t 
 
 #include "gemm_persist.cuh"
 #include "gemm_mc.cuh"
+#include "gemm_2cta.cuh"
 
 namespace ttb {
 
@@ -405,6 +430,10 @@ extern "C" int ttb_gemm(const TtbGemmArgs* gp, void* stream) {
     if (bn == 64) return g.cluster == 4 ? launch_mc<64, 4, 4>(g, ep, st) : launch_mc<64, 4, 2>(g, ep, st);
     return g.cluster == 4 ? launch_mc<128, 3, 4>(g, ep, st) : launch_mc<128, 3, 2>(g, ep, st);
   }
+  if (g.variant == 6) {         // CTA-pair (cta_group::2) kernel: round-2 experiment, see gemm_2cta.cuh
+    if (g.splitk > 1) { set_error("ttb_gemm: the CTA-pair kernel has no split-K"); return -1; }
+    return g.tile_n == 128 ? launch_2cta<128, 6>(g, ep, st) : launch_2cta<256, 6>(g, ep, st);
+  }
   static int persist = -1;   // TTB_GEMM_PERSIST=0 selects the one-tile-per-CTA kernels (A/B comparison)
   if (persist < 0) { const char* e = getenv("TTB_GEMM_PERSIST"); persist = e ? atoi(e) : 1; }
   // Measured on B200 (profiles/op_profile_r01_*): the persistent kernel wins when there are several tiles per SM
@@ -439,5 +468,6 @@ extern "C" int ttb_gemm(const TtbGemmArgs* gp, void* stream) {
   // (measured on B200: 1 CTA/SM with 256-wide tiles is slower than 2 CTAs/SM with 128-wide ones, so only on request)
   (void)tiles256;
   if (g.tile_n == 256) return launch_tc<256, 3>(g, ep, st);
+  if (g.variant == 5) return launch_tc<128, 3, true>(g, ep, st);     // two TMA issuers (round-2 experiment)
   return launch_tc<128, 3>(g, ep, st);
 }
