@@ -35,7 +35,11 @@ struct FaSmem {
   static constexpr int TOTAL = BAR_OFF + 16 * 8 + 1024;
 };
 
-template <int MINB>
+// DBUF (round-2 experiment, TTB_FA_DBUF=1, not yet run on hardware): S is double-buffered in TMEM and Q K_{j+1}^T is
+// issued BEFORE the MMA thread waits for P_j, so the softmax of tile j overlaps the score MMA of tile j+1 instead of
+// waiting behind [P V_j, Q K_{j+1}^T]. The softmax threads then wait for o_full(j-1) themselves before they touch O
+// (lazy rescale) or overwrite the single P buffer. With DBUF = false the kernel is unchanged.
+template <int MINB, bool DBUF = false>
 __global__ void __launch_bounds__(FA_THREADS, MINB)
 flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                      const __grid_constant__ CUtensorMap map_v, TtbAttnArgs a) {
@@ -47,10 +51,11 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint64_t* q_full = bars + 0;
   uint64_t* kv_full = bars + 1;            // [FA_STAGES]
   uint64_t* kv_empty = bars + 1 + FA_STAGES;
-  uint64_t* s_full = bars + 1 + 2 * FA_STAGES;
-  uint64_t* p_full = s_full + 1;
-  uint64_t* o_full = s_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 3);
+  constexpr int NS = DBUF ? 2 : 1;         // score buffers in TMEM
+  uint64_t* s_full = bars + 1 + 2 * FA_STAGES;   // [NS]
+  uint64_t* p_full = s_full + NS;
+  uint64_t* o_full = s_full + NS + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + NS + 2);
   float* sbias = reinterpret_cast<float*>(smem + FaSmem::BIAS_OFF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -71,18 +76,18 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     tma_prefetch_desc(&map_v);
     mbar_init(q_full, 1);
     for (int s = 0; s < FA_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(s_full, 1);
+    for (int b = 0; b < NS; ++b) mbar_init(&s_full[b], 1);
     mbar_init(p_full, 128);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  if (warp == 1) tmem_alloc<DBUF ? 256 : 128>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;        // columns [0, 64)
-  const uint32_t tmem_o = tmem_base + 64;   // columns [64, 128)
+  const uint32_t tmem_s = tmem_base;                        // columns [0, 64) (+ [64, 128) with DBUF)
+  const uint32_t tmem_o = tmem_base + (DBUF ? 128 : 64);    // 64 columns
 
   if (warp == 0) {
     if (lane == 0) {
@@ -107,6 +112,42 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       const uint32_t sp = smem_u32(smem + FaSmem::P_OFF);
       mbar_wait(q_full, 0);
       int stage = 0; uint32_t phase = 0;
+      if constexpr (DBUF) {
+        // S_0 first; then per tile: S_{j+1} (other score buffer, next KV stage) BEFORE waiting for P_j, then P V_j
+        mbar_wait(&kv_full[0], 0);
+        tc_fence_after();
+        {
+          const uint32_t sk = smem_u32(smem + FaSmem::KV_OFF);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(tmem_s, umma_desc_kmajor_sw128(sq + k * 32), umma_desc_kmajor_sw128(sk + k * 32), idesc_s, k != 0);
+          umma_commit(&s_full[0]);
+        }
+        for (int j = 0; j < ntiles; ++j) {
+          const int nstage = (stage + 1 == FA_STAGES) ? 0 : stage + 1;
+          const uint32_t nphase = (stage + 1 == FA_STAGES) ? (phase ^ 1) : phase;
+          if (j + 1 < ntiles) {
+            // score buffer (j+1)&1 was last read by the softmax of tile j-1, which arrived on p_full(j-1) afterwards
+            mbar_wait(&kv_full[nstage], nphase);
+            tc_fence_after();
+            const uint32_t sk = smem_u32(smem + FaSmem::KV_OFF + nstage * (FaSmem::K_BYTES + FaSmem::V_BYTES));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ss(tmem_s + (uint32_t)(((j + 1) & 1) * 64), umma_desc_kmajor_sw128(sq + k * 32),
+                           umma_desc_kmajor_sw128(sk + k * 32), idesc_s, k != 0);
+            umma_commit(&s_full[(j + 1) & 1]);
+          }
+          mbar_wait(p_full, j & 1);
+          tc_fence_after();
+          const uint32_t sv = smem_u32(smem + FaSmem::KV_OFF + stage * (FaSmem::K_BYTES + FaSmem::V_BYTES)) + FaSmem::K_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(tmem_o, umma_desc_kmajor_sw128(sp + k * 32), umma_desc_mnmajor_sw128(sv + k * 2048, 0), idesc_o, (j | k) != 0);
+          umma_commit(o_full);
+          umma_commit(&kv_empty[stage]);
+          stage = nstage; phase = nphase;
+        }
+      } else
       for (int j = 0; j < ntiles; ++j) {
         mbar_wait(&kv_full[stage], phase);
         tc_fence_after();
@@ -160,11 +201,12 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-      mbar_wait(s_full, j & 1);     // S_j ready; every earlier MMA (incl. P V of tile j-1) has retired
+      // S_j ready (without DBUF this also means that every earlier MMA, incl. P V of tile j-1, has retired)
+      mbar_wait(&s_full[DBUF ? (j & 1) : 0], DBUF ? ((j >> 1) & 1) : (j & 1));
       tc_fence_after();
       uint32_t r0[32], r1[32];
-      tmem_ld_32x32b_x32(tmem_s + lane_base, r0);
-      tmem_ld_32x32b_x32(tmem_s + lane_base + 32, r1);
+      tmem_ld_32x32b_x32(tmem_s + (DBUF ? (uint32_t)((j & 1) * 64) : 0u) + lane_base, r0);
+      tmem_ld_32x32b_x32(tmem_s + (DBUF ? (uint32_t)((j & 1) * 64) : 0u) + lane_base + 32, r1);
       tmem_ld_wait();
       float mx = -INFINITY;
       if (fast) {
@@ -183,6 +225,10 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           if (c < 32) r0[c] = __float_as_uint(v); else r1[c - 32] = __float_as_uint(v);
           mx = fmaxf(mx, v);
         }
+      }
+      if constexpr (DBUF) {
+        // O (lazy rescale below) and the P buffer belong to P V_{j-1} until it has retired
+        if (j > 0) { mbar_wait(o_full, (j - 1) & 1); tc_fence_after(); }
       }
       const bool grow = mx > m + 8.0f;                 // also true for the first finite max (m = -inf)
       const float m_new = grow ? mx : m;
@@ -269,7 +315,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<128>(tmem_base);
+    tmem_dealloc<DBUF ? 256 : 128>(tmem_base);
   }
 }
 
@@ -300,6 +346,21 @@ int flash_attention_launch(const TtbAttnArgs& a, cudaStream_t st) {
     mv = mk;
   }
   if (a.lse && !a.out_f32) { set_error("flash attention: lse output needs out_f32"); return -1; }
+  static int dbuf = -1;
+  if (dbuf < 0) { const char* e = getenv("TTB_FA_DBUF"); dbuf = (e && e[0] == '1') ? 1 : 0; }
+  if (dbuf) {
+    static bool attr = false;
+    if (!attr) {
+      cudaError_t r = cudaFuncSetAttribute(flash_attn_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FaSmem::TOTAL);
+      if (r != cudaSuccess) return check_cuda(r, "cudaFuncSetAttribute(flash_attn dbuf)");
+      attr = true;
+    }
+    dim3 grid_d((a.T + FA_BM - 1) / FA_BM, a.H, a.nseq);
+    const cudaError_t led = launch_pdl(flash_attn_tc_kernel<2, true>, grid_d, dim3(FA_THREADS), (size_t)FaSmem::TOTAL, st, mq, mk, mv, a);
+    if (led != cudaSuccess) return check_cuda(led, "flash_attn_tc_kernel<dbuf> launch");
+    TTB_CHECK_LAUNCH("flash_attn_tc_kernel<dbuf>");
+    return 0;
+  }
   static int occ = 0;
   if (!occ) {
     const char* e = getenv("TTB_FA_OCC");       // CTAs per SM the kernel is compiled for (register cap): 2 (default) or 3
