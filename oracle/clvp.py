@@ -6,7 +6,6 @@ clvp.py:99-140 and the x-transformers Encoder configuration the reference instan
 dim 32 applied to q, k AND v (625-629, 264-286), softmax(q k^T / 8), GEGLU feed-forward with
 erf-GELU (429-474), final LayerNorm (1234), masked mean with an all-ones mask (clvp.py:15-17).
 """
-import math
 
 import torch
 import torch.nn.functional as F

@@ -1,5 +1,4 @@
 """GPU: individual kernels behind the C-ABI against PyTorch fp32 / the oracle on the same inputs."""
-import math
 
 import pytest
 import torch
