@@ -148,6 +148,41 @@ int ttb_ar_fix_codes(int* codes, int B, int L, int stop_token, int* trim_len, vo
 int ttb_embed(const int* ids, const int* pos, int n, int D, const float* table, const float* pos_table, float* out,
               void* stream);
 
+/* ---- whole decode step as ONE persistent kernel (csrc/ar_step.cu) ----
+ * GPT2InferenceModel.forward for one new token of every candidate (models/autoregressive.py:108-186 + the HF GPT2Block
+ * stack + final_norm + mel_head): embed -> L x {ln_1, c_attn, attention over [shared prompt | own KV] with KV append,
+ * c_proj, ln_2, c_fc + gelu_new, mlp.c_proj} -> ln_f -> final_norm -> mel_head, written to `logits`. The sampler
+ * (ttb_ar_sample) consumes `logits` as before. KV layout differs from ttb_ar_decode_attention: K and V of a position are
+ * adjacent, prefix_kv bf16 [L][H][P][2][64] (ttb_ar_step_store_prefix), cand_kv bf16 [L][B][H][Nmax][2][64]. */
+typedef struct TtbArStepLayer {      /* device pointers of one GPT-2 block; weights bf16 K-major [out, in] */
+  const void *wqkv, *wproj, *wfc, *wproj2;
+  const float *ln1_g, *ln1_b, *bqkv, *bproj, *ln2_g, *ln2_b, *bfc, *bproj2;
+} TtbArStepLayer;
+typedef struct TtbArStepArgs {
+  int B, D, H, L, V, P, Nmax, pos_mode;    /* candidates (<= 256), width (= 64 H, <= 1024), heads, layers, vocab, prompt
+                                              positions (<= 352), KV slots per candidate, position rule (ttb_ar_embed_step) */
+  const TtbArStepLayer* layers;            /* HOST array [L]; read by ttb_ar_step_setup only */
+  const void* w_head; const float* b_head; /* mel_head bf16 [V, D], fp32 [V] */
+  const float *lnf_g, *lnf_b, *fn_g, *fn_b;
+  const float *mel_emb, *mel_pos;          /* fp32 tables */
+  const int* codes; int ld_codes;          /* sampled tokens [B, ld_codes]; the token fed is codes[b, step-1] */
+  TtbArState* state;                       /* state->reserved[0] != 0 after a launch = internal time-out (protocol error) */
+  float* x;                                /* fp32 [B, D] residual stream (workspace) */
+  void *a, *qkv, *o, *h, *hn;              /* bf16 workspaces [B, D], [B, 3D], [B, D], [B, 4D], [B, D] */
+  float* part;                             /* fp32 split-K scratch, ttb_ar_step_workspace() floats */
+  float* logits;                           /* fp32 [B, V] */
+  const void* prefix_kv; void* cand_kv;
+  void* tables;                            /* device, ttb_ar_step_workspace() bytes; filled by ttb_ar_step_setup */
+  void* sync;                              /* device, ttb_ar_step_workspace() bytes; zeroed by ttb_ar_step_setup */
+  int debug_layer_begin, debug_layer_end;  /* debug_layer_end > 0: run layers [begin, end) only */
+  int debug_phase_mask;                    /* != 0: subset of phases (bit 0 embed+ln_1, 1 c_attn, 2 attention, 3 c_proj, 4 ln_2,
+                                              5 c_fc, 6 mlp.c_proj, 7 next ln_1 / final norms, 8 mel_head) - tests and probes */
+} TtbArStepArgs;
+int ttb_ar_step_workspace(const TtbArStepArgs* args, long long* part_floats, long long* table_bytes, long long* sync_bytes);
+int ttb_ar_step_setup(const TtbArStepArgs* args, void* stream);      /* synchronous; once per (weights, workspace, B) */
+int ttb_ar_decode_step(const TtbArStepArgs* args, void* stream);     /* one launch; CUDA-graph capturable */
+int ttb_ar_step_store_prefix(const void* qkv, int P, int H, void* prefix_kv, void* stream);
+
 /* ---------------------------------------------------------------- CLVP */
 /* rotary (dim 32) on the first 32 dims of every head of q, k AND v (xtransformers.py:625-629,264-286);
  * qkv bf16 [nseq*T, 3*H*64] in place. */

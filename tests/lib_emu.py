@@ -149,6 +149,58 @@ def ar_store_prefix(qkv, P, H, pk, pv):
     _v(pv, (H, P, 64), (P * 64, 64, 1)).copy_(r[:, 2 * D:].reshape(P, H, 64).transpose(0, 1))
 
 
+def ar_step_store_prefix(qkv, P, H, pkv):
+    D = H * 64
+    r = _v(qkv, (P, 3 * D), (3 * D, 1))
+    o = _v(pkv, (H, P, 2, 64), (P * 128, 128, 64, 1))
+    o[:, :, 0].copy_(r[:, D:2 * D].reshape(P, H, 64).transpose(0, 1))
+    o[:, :, 1].copy_(r[:, 2 * D:].reshape(P, H, 64).transpose(0, 1))
+
+
+def ar_step_supported(B, D, H, P):
+    return 0 < B <= 256 and 0 < P <= 352 and D == 64 * H and D % 128 == 0 and D <= 1024
+
+
+class ArStep:
+    """Emulation of the one-kernel decode step (csrc/ar_step.cu): same arguments, same buffers, same KV layout."""
+
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def step(self, phase_mask=0, layer_begin=0, layer_end=0):
+        k = self.kw
+        B, D, H, L, V, P, Nmax = k["B"], k["D"], k["H"], k["L"], k["V"], k["P"], k["Nmax"]
+        assert phase_mask == 0 and layer_end == 0, "the emulation runs whole steps only"
+        st = k["state"]
+        j = int(st[0])
+        slot = j - 1
+        tok = k["codes"].view(B, k["ld_codes"])[:, j - 1].long()
+        x = k["mel_emb"][tok] + k["mel_pos"][j + 1 if k["pos_mode"] else j]
+
+        def ln(v, g, b):
+            return F.layer_norm(v, (D,), g, b, 1e-5)
+
+        def mm(a, w, b=None):                       # bf16 operands, fp32 accumulate
+            y = a.to(torch.bfloat16).float() @ w.float().t()
+            return y if b is None else y + b
+        pkv = k["prefix_kv"].view(L, H, P, 2, 64)
+        ckv = k["cand_kv"].view(L, B, H, Nmax, 2, 64)
+        for l, lw in enumerate(k["layers"]):
+            qkv = mm(ln(x, lw["ln1_g"], lw["ln1_b"]), lw["wqkv"], lw["bqkv"]).to(torch.bfloat16)
+            ckv[l, :, :, slot, 0] = qkv[:, D:2 * D].reshape(B, H, 64)
+            ckv[l, :, :, slot, 1] = qkv[:, 2 * D:].reshape(B, H, 64)
+            q = qkv[:, :D].reshape(B, H, 1, 64).float() * 0.125
+            Kc = torch.cat([pkv[l, :, :, 0].float().unsqueeze(0).expand(B, -1, -1, -1), ckv[l, :, :, :slot + 1, 0].float()], 2)
+            Vc = torch.cat([pkv[l, :, :, 1].float().unsqueeze(0).expand(B, -1, -1, -1), ckv[l, :, :, :slot + 1, 1].float()], 2)
+            o = (torch.softmax(q @ Kc.transpose(-1, -2), -1) @ Vc).reshape(B, D).to(torch.bfloat16)
+            x = x + mm(o, lw["wproj"], lw["bproj"])
+            hmid = F.gelu(mm(ln(x, lw["ln2_g"], lw["ln2_b"]), lw["wfc"], lw["bfc"]), approximate="tanh").to(torch.bfloat16)
+            x = x + mm(hmid, lw["wproj2"], lw["bproj2"])
+        hn = ln(ln(x, k["lnf_g"], k["lnf_b"]), k["fn_g"], k["fn_b"])
+        k["x"].view(B, D).copy_(x)
+        k["logits"].view(B, V).copy_(mm(hn, k["w_head"], k["b_head"]))
+
+
 def ar_sample(logits, ld_logits, V, B, uniforms, ld_u, seen, codes, ld_codes, finished, state, temperature, top_k,
               top_p, rep_penalty, stop_token, advance=True):
     from oracle.ar import sample_step
@@ -338,7 +390,7 @@ def install():
     for name in dir(me):
         if name.startswith("_") or name in ("install", "torch", "F", "math"):
             continue
-        if hasattr(real, name) and callable(getattr(me, name)):
+        if hasattr(real, name) and (callable(getattr(me, name)) or isinstance(getattr(me, name), type)):
             saved[name] = getattr(real, name)
             setattr(real, name, getattr(me, name))
     return saved

@@ -58,6 +58,9 @@ class AREngine:
     DECODE_CLUSTER = int(_os.environ.get("TTB_AR_CLUSTER", "0"))
     # TTB_AR_WIDE=1: c_attn / c_fc (N = 3D, 4D: one wave of 64-wide tiles) use 64-column tiles with an 8-stage pipeline
     DECODE_WIDE = int(_os.environ.get("TTB_AR_WIDE", "0"))
+    # TTB_AR_FUSED=1 (default): the decode step is ONE persistent kernel (csrc/ar_step.cu) + the sampler; 0 = the round-1
+    # per-op CUDA graph (kept as the A/B baseline and for shapes the fused kernel does not cover)
+    FUSED = int(_os.environ.get("TTB_AR_FUSED", "1"))
     SPLITK_PROJ = 2     # attn.c_proj  (K = D):   32 n-tiles x 2 m-tiles x 2 splits = 128 CTAs at D=1024, B=256
     SPLITK_PROJ2 = 4    # mlp.c_proj   (K = 4D):  32 x 2 x 4 = 256 CTAs
 
@@ -110,7 +113,10 @@ class AREngine:
         ws = st["pws"]
         for l, lw in enumerate(self.w.layers):
             def attn(qkv, o, l=l):
-                lib.ar_store_prefix(qkv, P, H, st["pk"][l], st["pv"][l])
+                if st["fused"]:
+                    lib.ar_step_store_prefix(qkv, P, H, st["pkv"][l])
+                else:
+                    lib.ar_store_prefix(qkv, P, H, st["pk"][l], st["pv"][l])
                 lib.attention(qkv, o, nseq=1, T=P, H=H, ld=3 * D, ldo=D, k_off=D, v_off=2 * D, scale=0.125, causal=True)
             self._layer(lw, x, P, ws, attn)
         lib.layernorm(x[P - 1:], 1, D, self.w.lnf_g, self.w.lnf_b, self.w.fn_g, self.w.fn_b, out_bf16=st["hn"][:1])
@@ -126,10 +132,16 @@ class AREngine:
         st = dict(key=key, P=P, B=B, Nmax=Nmax)
         st["px"] = torch.empty(P, D, dtype=torch.float32, device=dev)
         st["pws"] = self._alloc_trunk(P)
-        st["pk"] = torch.empty(L, H, P, 64, dtype=torch.bfloat16, device=dev)
-        st["pv"] = torch.empty(L, H, P, 64, dtype=torch.bfloat16, device=dev)
-        st["ck"] = torch.zeros(L, B, H, Nmax, 64, dtype=torch.bfloat16, device=dev)
-        st["cv"] = torch.zeros(L, B, H, Nmax, 64, dtype=torch.bfloat16, device=dev)
+        st["fused"] = bool(self.FUSED) and lib.ar_step_supported(B, D, H, P)
+        if st["fused"]:
+            # K and V of a position adjacent: one (candidate, head) stream is one contiguous byte range (csrc/ar_step.cu)
+            st["pkv"] = torch.empty(L, H, P, 2, 64, dtype=torch.bfloat16, device=dev)
+            st["ckv"] = torch.zeros(L, B, H, Nmax, 2, 64, dtype=torch.bfloat16, device=dev)
+        else:
+            st["pk"] = torch.empty(L, H, P, 64, dtype=torch.bfloat16, device=dev)
+            st["pv"] = torch.empty(L, H, P, 64, dtype=torch.bfloat16, device=dev)
+            st["ck"] = torch.zeros(L, B, H, Nmax, 64, dtype=torch.bfloat16, device=dev)
+            st["cv"] = torch.zeros(L, B, H, Nmax, 64, dtype=torch.bfloat16, device=dev)
         st["x"] = torch.empty(B, D, dtype=torch.float32, device=dev)
         st["ws"] = self._alloc_trunk(B)
         st["hn"] = torch.empty(max(B, 1), D, dtype=torch.bfloat16, device=dev)
@@ -145,13 +157,33 @@ class AREngine:
         st["uniforms"] = torch.empty(B, Nmax, dtype=torch.float32, device=dev)
         st["graph"] = None
         st["graph_params"] = None
+        st["step_handles"] = {}
         self._dec = st
         return st
+
+    def _step_handle(self, st, pos_mode):
+        """The one-kernel decode step bound to this workspace (tensor maps are built once per workspace + position rule)."""
+        hd = st["step_handles"].get(pos_mode)
+        if hd is None:
+            w, ws = self.w, st["ws"]
+            hd = lib.ArStep(B=st["B"], D=self.D, H=self.H, L=self.cfg.ar_layers, V=self.V, P=st["P"], Nmax=st["Nmax"],
+                            pos_mode=pos_mode, layers=w.layers, w_head=w.w_head, b_head=w.b_head, lnf_g=w.lnf_g,
+                            lnf_b=w.lnf_b, fn_g=w.fn_g, fn_b=w.fn_b, mel_emb=w.mel_emb, mel_pos=w.mel_pos,
+                            codes=st["codes"], ld_codes=st["Nmax"], state=st["state"], x=st["x"], a=ws["a"], qkv=ws["qkv"],
+                            o=ws["o"], h=ws["h"], hn=st["hn"], logits=st["logits"], prefix_kv=st["pkv"], cand_kv=st["ckv"])
+            st["step_handles"][pos_mode] = hd
+        return hd
 
     def _decode_step(self, st, sp):
         """One trunk pass for the last sampled token of every candidate + fused sampling of the next one."""
         B, P, Nmax, D, H = st["B"], st["P"], st["Nmax"], self.D, self.H
         x, ws = st["x"], st["ws"]
+        if st["fused"]:
+            self._step_handle(st, sp["pos_mode"]).step()
+            lib.ar_sample(st["logits"], self.V, self.V, B, st["uniforms"], Nmax, st["seen"], st["codes"], Nmax,
+                          st["finished"], st["state"], sp["temperature"], sp["top_k"], sp["top_p"], sp["rep_penalty"],
+                          self.cfg.stop_mel_token, advance=True)
+            return
         lib.ar_embed_step(st["codes"], Nmax, st["state"], self.w.mel_emb, self.w.mel_pos, B, D, sp["pos_mode"], x)
         # Skinny-M decode (M = B candidates): every GEMM is weight-streaming bound, so the grid is widened with
         # 32-column tiles and, for the two GEMMs that feed the residual stream, split-K; their partial sums, bias and
@@ -257,6 +289,10 @@ class AREngine:
                     self._decode_step(st, sp)
                     if trace_logits is not None:
                         trace_logits.append(st["logits"].clone())
+        if st["fused"] and steps > 0:
+            flag = int(st["state"][2].item())      # TtbArState.reserved[0]: set by a timed-out wait inside the step kernel
+            if flag:
+                raise lib.TtbError("ar_step_kernel: internal wait timed out (code %d); results are invalid" % flag)
         return st["codes"].clone()
 
     # ------------------------------------------------------------------ teacher-forced passes

@@ -45,6 +45,23 @@ class DiffStepArgs(C.Structure):
                 ("cond_free", C.c_int), ("cond_free_k", C.c_float), ("mel_out", C.c_void_p)]
 
 
+class ArStepLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("wqkv", "wproj", "wfc", "wproj2", "ln1_g", "ln1_b", "bqkv", "bproj", "ln2_g",
+                                          "ln2_b", "bfc", "bproj2")]
+
+
+class ArStepArgs(C.Structure):
+    _fields_ = [("B", C.c_int), ("D", C.c_int), ("H", C.c_int), ("L", C.c_int), ("V", C.c_int), ("P", C.c_int),
+                ("Nmax", C.c_int), ("pos_mode", C.c_int),
+                ("layers", C.POINTER(ArStepLayer)), ("w_head", C.c_void_p), ("b_head", C.c_void_p),
+                ("lnf_g", C.c_void_p), ("lnf_b", C.c_void_p), ("fn_g", C.c_void_p), ("fn_b", C.c_void_p),
+                ("mel_emb", C.c_void_p), ("mel_pos", C.c_void_p), ("codes", C.c_void_p), ("ld_codes", C.c_int),
+                ("state", C.c_void_p), ("x", C.c_void_p), ("a", C.c_void_p), ("qkv", C.c_void_p), ("o", C.c_void_p),
+                ("h", C.c_void_p), ("hn", C.c_void_p), ("part", C.c_void_p), ("logits", C.c_void_p),
+                ("prefix_kv", C.c_void_p), ("cand_kv", C.c_void_p), ("tables", C.c_void_p), ("sync", C.c_void_p),
+                ("debug_layer_begin", C.c_int), ("debug_layer_end", C.c_int), ("debug_phase_mask", C.c_int)]
+
+
 _lib = None
 
 # every symbol include/ttb.h declares (checked by tests/test_capi_symbols.py)
@@ -55,6 +72,7 @@ SYMBOLS = [
     "ttb_timestep_embedding", "ttb_linear_small", "ttb_interp_nearest", "ttb_diffusion_step", "ttb_counter_add",
     "ttb_transpose_f32", "ttb_cast_pad_bf16", "ttb_broadcast_rows", "ttb_voc_conv1d", "ttb_voc_convt",
     "ttb_voc_lvc_gate", "ttb_voc_to_tokens_bf16", "ttb_debug_gemm_trace",
+    "ttb_ar_step_workspace", "ttb_ar_step_setup", "ttb_ar_decode_step", "ttb_ar_step_store_prefix",
 ]
 
 
@@ -184,6 +202,58 @@ def ar_decode_attention(qkv, pk, pv, ck, cv, state, B, H, P, Nmax, out, scratch_
 
 def ar_store_prefix(qkv, P, H, pk, pv):
     _chk(load().ttb_ar_store_prefix(_p(_bf(qkv)), P, H, _p(_bf(pk)), _p(_bf(pv)), _stream()), "ttb_ar_store_prefix")
+
+
+def ar_step_store_prefix(qkv, P, H, pkv):
+    _chk(load().ttb_ar_step_store_prefix(_p(_bf(qkv)), P, H, _p(_bf(pkv)), _stream()), "ttb_ar_step_store_prefix")
+
+
+AR_STEP_MAX_B, AR_STEP_MAX_P, AR_STEP_MAX_D = 256, 352, 1024    # limits of csrc/ar_step.cu (make_plan)
+
+
+def ar_step_supported(B, D, H, P):
+    return 0 < B <= AR_STEP_MAX_B and 0 < P <= AR_STEP_MAX_P and D == 64 * H and D % 128 == 0 and D <= AR_STEP_MAX_D
+
+
+class ArStep:
+    """Handle of the one-kernel decode step (include/ttb.h TtbArStepArgs): owns the scratch / table / sync buffers and
+    keeps every tensor the kernel points at alive. `layers`: list of dicts with the keys of ARWeights.layers."""
+
+    def __init__(self, *, B, D, H, L, V, P, Nmax, pos_mode, layers, w_head, b_head, lnf_g, lnf_b, fn_g, fn_b, mel_emb,
+                 mel_pos, codes, ld_codes, state, x, a, qkv, o, h, hn, logits, prefix_kv, cand_kv):
+        dev = x.device
+        self._keep = (layers, w_head, b_head, lnf_g, lnf_b, fn_g, fn_b, mel_emb, mel_pos, codes, state, x, a, qkv, o, h,
+                      hn, logits, prefix_kv, cand_kv)
+        self._larr = (ArStepLayer * L)()
+        for i, lw in enumerate(layers):
+            for n in ("wqkv", "wproj", "wfc", "wproj2"):
+                setattr(self._larr[i], n, _bf(lw[n]).data_ptr())
+            for n in ("ln1_g", "ln1_b", "bqkv", "bproj", "ln2_g", "ln2_b", "bfc", "bproj2"):
+                setattr(self._larr[i], n, _f32(lw[n]).data_ptr())
+        g = ArStepArgs()
+        g.B, g.D, g.H, g.L, g.V, g.P, g.Nmax, g.pos_mode = B, D, H, L, V, P, Nmax, pos_mode
+        g.layers = C.cast(self._larr, C.POINTER(ArStepLayer))
+        g.w_head, g.b_head = _bf(w_head).data_ptr(), _f32(b_head).data_ptr()
+        g.lnf_g, g.lnf_b, g.fn_g, g.fn_b = lnf_g.data_ptr(), lnf_b.data_ptr(), fn_g.data_ptr(), fn_b.data_ptr()
+        g.mel_emb, g.mel_pos = _f32(mel_emb).data_ptr(), _f32(mel_pos).data_ptr()
+        g.codes, g.ld_codes, g.state = codes.data_ptr(), ld_codes, state.data_ptr()
+        g.x, g.a, g.qkv, g.o = _f32(x).data_ptr(), _bf(a).data_ptr(), _bf(qkv).data_ptr(), _bf(o).data_ptr()
+        g.h, g.hn, g.logits = _bf(h).data_ptr(), _bf(hn).data_ptr(), _f32(logits).data_ptr()
+        g.prefix_kv, g.cand_kv = _bf(prefix_kv).data_ptr(), _bf(cand_kv).data_ptr()
+        pf, tb, sb = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
+        _chk(load().ttb_ar_step_workspace(C.byref(g), C.byref(pf), C.byref(tb), C.byref(sb)), "ttb_ar_step_workspace")
+        self.part = torch.zeros(max(pf.value, 4), dtype=torch.float32, device=dev)
+        self.tables = torch.zeros(tb.value, dtype=torch.uint8, device=dev)
+        self.sync = torch.zeros(sb.value, dtype=torch.uint8, device=dev)
+        g.part, g.tables, g.sync = self.part.data_ptr(), self.tables.data_ptr(), self.sync.data_ptr()
+        self.args = g
+        _chk(load().ttb_ar_step_setup(C.byref(g), _stream()), "ttb_ar_step_setup")
+
+    def step(self, phase_mask=0, layer_begin=0, layer_end=0):
+        """One decode step (all phases by default; phase_mask / layer range select a part, for tests and probes)."""
+        g = self.args
+        g.debug_phase_mask, g.debug_layer_begin, g.debug_layer_end = phase_mask, layer_begin, layer_end
+        _chk(load().ttb_ar_decode_step(C.byref(g), _stream()), "ttb_ar_decode_step")
 
 
 def ar_sample(logits, ld_logits, V, B, uniforms, ld_u, seen, codes, ld_codes, finished, state, temperature, top_k,
