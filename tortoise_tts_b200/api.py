@@ -53,11 +53,14 @@ def pad_or_truncate(t, length):
 
 
 class _Tokenizer:
-    """VoiceBpeTokenizer.encode (utils/tokenizer.py:172-185) with the basic cleaner chain. The BPE vocabulary is the
-    reference's data/tokenizer.json (an asset, not code): pass `tokenizer_vocab_file` or set TORTOISE_TOKENIZER_JSON."""
+    """VoiceBpeTokenizer (utils/tokenizer.py:172-197): `english_cleaners` by default, `basic_cleaners` with
+    `use_basic_cleaners` (the constructor's `tokenizer_basic`). The BPE vocabulary is the reference's data/tokenizer.json
+    (an asset, not code): pass `tokenizer_vocab_file` or set TORTOISE_TOKENIZER_JSON."""
 
-    def __init__(self, vocab_file=None):
+    def __init__(self, vocab_file=None, use_basic_cleaners=False):
         from tokenizers import Tokenizer
+        from . import cleaners
+        self.preprocess_text = cleaners.basic_cleaners if use_basic_cleaners else cleaners.english_cleaners
         vocab_file = vocab_file or os.environ.get("TORTOISE_TOKENIZER_JSON")
         if vocab_file is None or not os.path.exists(vocab_file):
             raise FileNotFoundError("tokenizer.json not found: pass tokenizer_vocab_file=... (reference asset "
@@ -65,10 +68,15 @@ class _Tokenizer:
         self.tok = Tokenizer.from_file(vocab_file)
 
     def encode(self, txt):
-        import re
-        txt = re.sub(r"\s+", " ", txt.lower()).replace('"', "")
+        txt = self.preprocess_text(txt)
         txt = txt.replace(" ", "[SPACE]")
         return self.tok.encode(txt).ids
+
+    def decode(self, seq):
+        if isinstance(seq, torch.Tensor):
+            seq = seq.cpu().numpy()
+        txt = self.tok.decode(seq, skip_special_tokens=False).replace(" ", "")
+        return txt.replace("[SPACE]", " ").replace("[STOP]", "").replace("[UNK]", "")
 
 
 class TextToSpeech:
@@ -85,8 +93,14 @@ class TextToSpeech:
         self.enable_redaction = False  # wav2vec redaction is out of scope
         self.kv_cache = kv_cache
         self.device = torch.device(device if device is not None else "cuda")
+        if self.device.type == "cuda":
+            # the kernels are enqueued on the CURRENT device's stream: make the engine's device current (weights,
+            # workspaces and launches must agree; reference api.py:202-205 only records the device)
+            torch.cuda.set_device(self.device if self.device.index is not None else torch.cuda.current_device())
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.cfg = config or ModelConfig.full()
         self._tok_file = tokenizer_vocab_file
+        self._tok_basic = bool(tokenizer_basic)
         self._tokenizer = None
         if state_dicts is None:
             state_dicts = {
@@ -104,11 +118,15 @@ class TextToSpeech:
     @property
     def tokenizer(self):
         if self._tokenizer is None:
-            self._tokenizer = _Tokenizer(self._tok_file)
+            self._tokenizer = _Tokenizer(self._tok_file, self._tok_basic)
         return self._tokenizer
 
     def deterministic_state(self, seed=None):
-        seed = int(time()) if seed is None else seed
+        if seed is None:
+            seed = int(time())
+            # every rank must derive the SAME candidates table / diffusion noise (the CFG pair mixes branches computed on
+            # two ranks against each rank's local x): rank 0's clock decides
+            seed = parallel.broadcast_seed(seed, self.device)
         torch.manual_seed(seed)
         random.seed(seed)
         return seed

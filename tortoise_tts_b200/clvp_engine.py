@@ -94,6 +94,15 @@ class CLVPEngine:
         tl = self.text_latent(text_tokens)
         out = torch.empty(B, dtype=torch.float32, device=dev)
         codes = codes.to(device=dev, dtype=torch.int32).contiguous()
+        # the embedding gather is unchecked on the device: an id outside the table (the AR vocabulary has two ids more
+        # than speech_emb: start 8192 / stop 8193) raises here as nn.Embedding does in the reference (clvp.py:114)
+        if B * L > 0:
+            lo, hi = int(codes.min().item()), int(codes.max().item())
+            if lo < 0 or hi >= self.speech_emb.shape[0]:
+                raise IndexError("CLVP speech token %d outside the embedding table [0, %d)" %
+                                 (hi if hi >= self.speech_emb.shape[0] else lo, self.speech_emb.shape[0]))
+        if any(int(t) < 0 or int(t) >= self.text_emb.shape[0] for t in text_tokens):
+            raise IndexError("CLVP text token outside the embedding table [0, %d)" % self.text_emb.shape[0])
         for b0 in range(0, B, chunk):
             nb = min(chunk, B - b0)
             pooled = self._encode(self.speech_enc, codes[b0:b0 + nb].reshape(-1), self.speech_emb, nb, L)

@@ -92,12 +92,30 @@ ar_sample_kernel(const float* __restrict__ logits, int ld_logits, int V, const f
     __syncthreads();
   }
   const uint32_t thr = s_prefix;  // key of the k-th largest; HF keeps everything >= it (ties included)
+  // values strictly above the threshold: at most top_k - 1 < SAMP_CAP of them, slot order is irrelevant (sorted below)
   for (int i = threadIdx.x; i < V; i += SAMP_THREADS) {
     const float s = sval[i];
-    if (f2key(s) >= thr) {
+    if (f2key(s) > thr) {
       const int slot = atomicAdd(&s_ncand, 1);
-      if (slot < SAMP_CAP) { cand_v[slot] = s; cand_i[slot] = i; }
+      cand_v[slot] = s; cand_i[slot] = i;
     }
+  }
+  __syncthreads();
+  // values equal to the threshold, in ASCENDING INDEX order (one warp, ballot compaction): if more than SAMP_CAP values
+  // tie (flat logits, duplicated mel_head rows) the survivors are the lowest ids - a fixed set, not a race
+  if (threadIdx.x < 32) {
+    int n = s_ncand;
+    for (int base = 0; base < V && n < SAMP_CAP; base += 32) {
+      const int i = base + threadIdx.x;
+      const bool tie = (i < V) && (f2key(sval[i]) == thr);
+      const unsigned m = __ballot_sync(0xffffffffu, tie);
+      if (tie) {
+        const int slot = n + __popc(m & ((1u << threadIdx.x) - 1u));
+        if (slot < SAMP_CAP) { cand_v[slot] = sval[i]; cand_i[slot] = i; }
+      }
+      n += __popc(m);
+    }
+    if (threadIdx.x == 0) s_ncand = n;
   }
   __syncthreads();
   if (threadIdx.x < 32) {

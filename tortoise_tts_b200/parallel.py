@@ -34,6 +34,17 @@ class single_rank:
         return False
 
 
+def broadcast_seed(seed, device):
+    """Rank 0's seed on every rank (one int64 broadcast); the identity without a process group."""
+    rank, ws = world()
+    if ws == 1:
+        return int(seed)
+    backend = dist.get_backend()
+    t = torch.tensor([int(seed)], dtype=torch.int64, device=device if backend == "nccl" else "cpu")
+    dist.broadcast(t, src=0)
+    return int(t.item())
+
+
 def shard_range(total, rank, world_size):
     """Contiguous, balanced split of `total` candidates: returns (lo, hi) for `rank`."""
     per = (total + world_size - 1) // world_size
