@@ -75,7 +75,9 @@ def test_groupnorm_fused(C, groups, S):
                                                       (64, 2, 1, False, False), (128, 2, 2, True, True),
                                                       (1872, 16, 2, False, True), (676, 16, 1, True, False),
                                                       (1872, 16, 2, False, "t5"), (500, 4, 1, True, "t5"),
-                                                      (300, 4, 2, False, "big")])
+                                                      (300, 4, 2, False, "big"), (256, 2, 1, True, True),
+                                                      (257, 3, 1, False, "t5"), (430, 12, 2, False, False),
+                                                      (193, 2, 2, True, False), (1000, 2, 1, True, "big")])
 def test_attention(T, H, nseq, causal, use_bias):
     from tortoise_tts_b200 import lib
     from tortoise_tts_b200.diffusion_engine import _rel_pos_table

@@ -307,6 +307,7 @@ extern "C" int ttb_attention(const TtbAttnArgs* ap, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (a.T <= 0 || a.nseq <= 0) return 0;
   if ((a.ld & 7) || (a.ldo & 7) || (a.k_off & 7) || (a.v_off & 7)) { set_error("ttb_attention: strides must be multiples of 8"); return -1; }
+  if (flash_attention2_supported(a)) return flash_attention2_launch(a, st);
   if (flash_attention_supported(a)) return flash_attention_launch(a, st);
   dim3 grid((a.T + ATT_Q - 1) / ATT_Q, a.H, a.nseq);
   attn_simt_kernel<<<grid, ATT_Q, 0, st>>>(a);
