@@ -111,6 +111,8 @@ typedef struct TtbAttnArgs {
   float* lse;           /* fp32 [nseq*T, H], log2 domain, or NULL */
   int bias_sat;         /* > 0: bias[h][r] == bias[h][-(T-1)] for r <= -bias_sat and == bias[h][T-1] for r >= bias_sat
                            (T5 buckets saturate at max_distance); lets far-from-diagonal tiles skip the table. 0 = unknown */
+  int head_dim;         /* 0 or 64: heads of 64 (tcgen05 kernels). 32 / 96 / 128: short sequences, packed form only; head h
+                           at column head_dim * h (diffusion contextual embedder: 2048 channels / 16 heads) */
 } TtbAttnArgs;
 /* softmax(q k^T * scale + bias) v per (sequence, head), head_dim 64. Replaces QKVAttentionLegacy
  * (arch_util.py:44-77), HF GPT2Attention._attn, and xtransformers Attention (xtransformers.py:660-712). */
@@ -225,6 +227,28 @@ int ttb_transpose_f32(const float* in, int R, int Cc, float* out, void* stream);
 /* fp32 [R, Cc] (row stride ld_in) -> bf16 [R, ncols_out] (row stride ldo), columns >= Cc zero-filled */
 int ttb_cast_pad_bf16(const float* in, int R, int Cc, int ld_in, void* out, int ldo, int ncols_out, void* stream);
 int ttb_broadcast_rows(const float* row, int R, int Cc, float* out_f32, void* out_bf16, int ldo, void* stream);
+
+/* ---------------------------------------------------------------- conditioning front-end (get_conditioning_latents) */
+/* torchaudio.functional.resample (api.py:284): polyphase FIR. kernels fp32 [up, klen] built on the host
+ * (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99); out[i*up + j] = sum_k xpad[i*down + k] * kernels[j][k],
+ * xpad = x preceded by `width` zeros. m = number of output samples wanted. */
+int ttb_audio_resample(const float* x, int n, const float* kernels, int down, int up, int klen, int width, float* out,
+                       int m, void* stream);
+/* STFT (center = True, reflect padding, hop) -> |.|^power -> mel filterbank -> log(max(., floor)) [/ div[c]].
+ * power 2 + div = mel_norms: TorchMelSpectrogram (arch_util.py:295-331); power 1 + clip: TacotronSTFT.mel_spectrogram
+ * (utils/audio.py:177-191, utils/stft.py:133-157). window fp32 [n_fft], twiddle fp32 [n_fft][2] = (cos, sin)(2 pi i / n_fft),
+ * fb fp32 [n_mels, n_fft/2+1]. Frames = 1 + n / hop. out_bf16 token-major [frames, ldo] (columns >= n_mels zeroed),
+ * out_f32 channel-major [n_mels, frames]; either may be NULL. */
+int ttb_audio_stft_mel(const float* x, int n, int n_fft, int hop, const float* window, const float* twiddle,
+                       const float* fb, int n_mels, int power, int clip, float floor_v, const float* div, void* out_bf16,
+                       int ldo, float* out_f32, void* stream);
+/* out[c] = (accumulate ? out[c] : 0) + scale * sum_r x[r*ld + c]  (means over positions / clips, autoregressive.py:451,
+ * diffusion_decoder.py:228-229) */
+int ttb_mean_rows(const float* x, int R, int C, int ld, float scale, int accumulate, float* out, void* stream);
+/* one row: out = leaky_relu(x @ (W*wscale)^T + b*bscale, slope) * gain  (EqualLinear / nn.Linear of RandomLatentConverter,
+ * random_latent_generator.py:21-50) */
+int ttb_equal_linear(const float* x, int K, const float* W, const float* b, int N, float wscale, float bscale, float slope,
+                     float gain, float* out, void* stream);
 
 /* ---------------------------------------------------------------- UnivNet vocoder (channel-major fp32 [C, L]) */
 /* Conv1d, small channel counts, zero or reflect padding, optional LeakyReLU on input/output, optional residual add

@@ -104,19 +104,20 @@ def groupnorm(x, B, S, Cc, groups, gamma, beta, partials, scale_shift=None, ss_b
         _v(out_f32, (B, S, Cc), (S * ldof, ldof, 1)).copy_(y)
 
 
-def attention(qkv, out, *, nseq, T, H, ld, ldo, k_off, v_off, scale, causal=False, bias=None, bias_sat=0):
+def attention(qkv, out, *, nseq, T, H, ld, ldo, k_off, v_off, scale, causal=False, bias=None, bias_sat=0, head_dim=0):
+    hd = head_dim or 64
     base = _v(qkv, (nseq, T, ld), (T * ld, ld, 1)).float()
-    q = base[..., :H * 64].reshape(nseq, T, H, 64).transpose(1, 2)
-    k = base[..., k_off:k_off + H * 64].reshape(nseq, T, H, 64).transpose(1, 2)
-    v = base[..., v_off:v_off + H * 64].reshape(nseq, T, H, 64).transpose(1, 2)
+    q = base[..., :H * hd].reshape(nseq, T, H, hd).transpose(1, 2)
+    k = base[..., k_off:k_off + H * hd].reshape(nseq, T, H, hd).transpose(1, 2)
+    v = base[..., v_off:v_off + H * hd].reshape(nseq, T, H, hd).transpose(1, 2)
     w = (q @ k.transpose(-1, -2)) * scale
     if bias is not None:
         i = torch.arange(T)
         w = w + bias[:, i[None, :] - i[:, None] + T - 1].unsqueeze(0)
     if causal:
         w = w.masked_fill(~torch.ones(T, T, dtype=torch.bool).tril(), float("-inf"))
-    o = (torch.softmax(w, -1) @ v).transpose(1, 2).reshape(nseq, T, H * 64)
-    _v(out, (nseq, T, H * 64), (T * ldo, ldo, 1)).copy_(o.to(torch.bfloat16))
+    o = (torch.softmax(w, -1) @ v).transpose(1, 2).reshape(nseq, T, H * hd)
+    _v(out, (nseq, T, H * hd), (T * ldo, ldo, 1)).copy_(o.to(torch.bfloat16))
 
 
 def ar_embed_step(codes, ld_codes, state, mel_emb, mel_pos, B, D, pos_mode, x):
@@ -375,6 +376,44 @@ def voc_to_tokens_bf16(x, Cc, L, out, ldo, split=False):
         o[:, :Cc] = hi
         o[:, Cc:2 * Cc] = (xt - hi.float()).to(torch.bfloat16)
         o[:, 2 * Cc:3 * Cc] = hi
+
+
+def audio_resample(x, n, kernels, down, up, klen, width, out, m):
+    xp = F.pad(x[:n].reshape(1, 1, -1), (width, width + down))
+    y = F.conv1d(xp, kernels.reshape(up, 1, klen), stride=down).transpose(1, 2).reshape(-1)
+    out[:m].copy_(y[:m])
+
+
+def audio_stft_mel(x, n, n_fft, hop, window, twiddle, fb, n_mels, power, clip, floor_v, div, out_bf16=None, ldo=0,
+                   out_f32=None):
+    v = x[:n].clamp(-1, 1) if clip else x[:n]
+    xp = F.pad(v.reshape(1, 1, -1), (n_fft // 2, n_fft // 2), mode="reflect").reshape(-1)
+    fr = xp.unfold(0, n_fft, hop) * window                      # [frames, n_fft]
+    idx = (torch.arange(n_fft // 2 + 1)[:, None] * torch.arange(n_fft)[None, :]) % n_fft
+    re = fr @ twiddle[:, 0][idx].t()
+    im = -(fr @ twiddle[:, 1][idx].t())
+    p2 = re * re + im * im
+    spec = p2 if power == 2 else p2.sqrt()
+    y = torch.log((spec @ fb.t()).clamp(min=floor_v))
+    if div is not None:
+        y = y / div
+    frames = y.shape[0]
+    if out_f32 is not None:
+        _v(out_f32, (n_mels, frames), (frames, 1)).copy_(y.t())
+    if out_bf16 is not None:
+        o = _v(out_bf16, (frames, ldo), (ldo, 1))
+        o.zero_()
+        o[:, :n_mels] = y.to(torch.bfloat16)
+
+
+def mean_rows(x, R, Cc, ld, scale, out, accumulate=False):
+    s = _v(x, (R, Cc), (ld, 1)).sum(0) * scale
+    out[:Cc].copy_(out[:Cc] + s if accumulate else s)
+
+
+def equal_linear(x, K, W, b, N, out, wscale=1.0, bscale=1.0, slope=1.0, gain=1.0):
+    y = x[:K] @ (W.reshape(N, K) * wscale).t() + (0 if b is None else b * bscale)
+    out[:N].copy_(F.leaky_relu(y, slope) * gain)
 
 
 def load():

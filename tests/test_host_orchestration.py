@@ -84,3 +84,31 @@ def test_vocoder_engine(env):
     wav = VocoderEngine(sds["vocoder"], cfg, device="cpu").inference(g["voc_mel"][0], g["voc_z"][0])
     err = (wav - g["voc_wav"][0, 0]).abs().max().item()
     assert err < 0.03, err
+
+
+def test_conditioning_engine(env):
+    """Conditioning front-end (tables, resampling bank, STFT framing, strided convs, clip / position means) against the
+    oracle, kernels emulated: catches host-side mistakes in table construction and layouts."""
+    from tortoise_tts_b200.conditioning_engine import ConditioningEngine, RandomLatentEngine
+    from tortoise_tts_b200.synth import synth_rlg
+    from oracle import conditioning as oc
+    cfg, sds, g = env
+    torch.manual_seed(4)
+    clips = [(torch.randn(1, n) * 0.2).clamp(-1, 1) for n in (140000, 60000)]
+    mel_norms = -(torch.rand(80) * 5 + 1)
+    eng = ConditioningEngine(sds["autoregressive"], sds["diffusion"], cfg, device="cpu", mel_norms=mel_norms)
+    starts = [23, None]
+    with torch.no_grad():
+        want_ar = oc.ar_conditioning_latent(sds["autoregressive"], cfg, clips, mel_norms, starts)
+        want_df = oc.diffusion_conditioning_latent(sds["diffusion"], cfg, clips)
+    got_ar, mels = eng.ar_latent(clips, starts, return_mels=True)
+    w0 = oc.format_conditioning_clip(clips[0], 23)
+    assert (mels[0, 0] - oc.torch_mel_spectrogram(w0, mel_norms)[0]).abs().max() < 2e-3
+    assert _rel(got_ar, want_ar) < 0.03
+    got_df, dmels = eng.diffusion_latent(clips, return_mels=True)
+    s0 = oc.resample_22k_24k(clips[0])[..., :oc.DIFF_COND_LENGTH]
+    assert (dmels[0, 0] - oc.tacotron_mel(s0)[0]).abs().max() < 2e-3
+    assert _rel(got_df, want_df) < 0.03
+    sd = synth_rlg(64, 0)
+    r = torch.randn(1, 64)
+    assert (RandomLatentEngine(sd, 64, "cpu")(r) - oc.random_latent(sd, r)).abs().max() < 1e-5

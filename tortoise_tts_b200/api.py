@@ -19,6 +19,7 @@ from .ar_engine import AREngine
 from .clvp_engine import CLVPEngine
 from .diffusion_engine import DiffusionEngine
 from .vocoder_engine import VocoderEngine
+from .conditioning_engine import ConditioningEngine, RandomLatentEngine
 from . import lib
 from . import parallel
 
@@ -50,6 +51,117 @@ def pad_or_truncate(t, length):
     if t.shape[-1] < length:
         return torch.nn.functional.pad(t, (0, length - t.shape[-1]))
     return t[..., :length]
+
+
+def _default_mel_norms():
+    """tortoise/data/mel_norms.pth (TorchMelSpectrogram's per-bin divisors): TORTOISE_MEL_NORMS (.pth) overrides the
+    packaged copy of the 80 numbers."""
+    p = os.environ.get("TORTOISE_MEL_NORMS")
+    if p:
+        return torch.load(p, map_location="cpu").float()
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "mel_norms.json")) as f:
+        return torch.tensor(json.load(f)["mel_norms"], dtype=torch.float32)
+
+
+class DiffuserSpec:
+    """What `load_discrete_vocoder_diffuser` (api.py:64-70) configures: the number of respaced steps of the 4000-step
+    linear schedule and the classifier-free-guidance setting. The schedule tables themselves live on the device inside
+    DiffusionEngine (same float64 construction as SpacedDiffusion, diffusion_engine.make_schedule)."""
+
+    def __init__(self, trained_diffusion_steps=4000, desired_diffusion_steps=200, cond_free=True, cond_free_k=1):
+        if trained_diffusion_steps != 4000:
+            raise ValueError("the engine's schedule is the reference's 4000-step linear schedule")
+        self.num_timesteps = int(desired_diffusion_steps)
+        self.conditioning_free = bool(cond_free)
+        self.conditioning_free_k = float(cond_free_k)
+
+
+def load_discrete_vocoder_diffuser(trained_diffusion_steps=4000, desired_diffusion_steps=200, cond_free=True, cond_free_k=1):
+    """≙ api.py:64-70."""
+    return DiffuserSpec(trained_diffusion_steps, desired_diffusion_steps, cond_free, cond_free_k)
+
+
+def format_conditioning(clip, cond_length=132300, device="cuda", engine=None):
+    """≙ api.py:73-84: clip [1, n] at 22.05 kHz -> MEL [1, 80, 517] (random crop via `random`, as the reference).
+    `engine`: a ConditioningEngine (TextToSpeech.conditioning); built on demand from the packaged mel_norms otherwise."""
+    if cond_length != 132300:
+        raise ValueError("cond_length is fixed at 132300 samples (the ConditioningEncoder's training length)")
+    if engine is None:
+        engine = _MelOnly(device)
+    w = ConditioningEngine.format_clip(clip.to(engine.dev).float()).contiguous()
+    mf = torch.empty(80, 1 + w.numel() // 256, dtype=torch.float32, device=engine.dev)
+    engine.ar_mel(w, mf)
+    return mf.unsqueeze(0)
+
+
+class _MelOnly(ConditioningEngine):
+    """The table part of ConditioningEngine (no encoder weights): enough for format_conditioning()."""
+
+    def __init__(self, device):
+        import numpy as np
+        from .conditioning_engine import _mel_filterbank, N_FFT
+        self.dev = torch.device(device)
+        n = np.arange(N_FFT)
+        self.window = torch.from_numpy(0.5 - 0.5 * np.cos(2.0 * np.pi * n / N_FFT)).float().to(self.dev)
+        tw = np.stack([np.cos(2.0 * np.pi * n / N_FFT), np.sin(2.0 * np.pi * n / N_FFT)], axis=1)
+        self.twiddle = torch.from_numpy(tw).float().contiguous().to(self.dev)
+        self.fb_ar = torch.from_numpy(_mel_filterbank(22050, N_FFT, 80, 0.0, 8000.0, "htk")).float().contiguous().to(self.dev)
+        self.mel_norms = _default_mel_norms().to(self.dev)
+        self.kpad_ar = 128
+
+
+def fix_autoregressive_output(codes, stop_token, complain=True):
+    """≙ api.py:87-114 on one row of codes (1-D integer tensor): in place on the device, returns the tensor."""
+    if codes.dim() != 1:
+        raise ValueError("fix_autoregressive_output works on one row of codes (api.py:87-114)")
+    work = codes.to(device="cuda", dtype=torch.int32).contiguous()
+    has_stop = bool((work == stop_token).any().item())
+    if not has_stop:
+        if complain:
+            print("No stop tokens found in one of the generated voice clips. This typically means the spoken audio is "
+                  "too long. In some cases, the output will still be good, though. Listen to it and if it is missing words, "
+                  "try breaking up your input text.")
+        return codes
+    lib.ar_fix_codes(work, 1, work.numel(), int(stop_token), None)
+    codes.copy_(work.to(device=codes.device, dtype=codes.dtype))
+    return codes
+
+
+def do_spectrogram_diffusion(diffusion_model, diffuser, latents, conditioning_latents, temperature=1, verbose=True):
+    """≙ api.py:117-130. diffusion_model: DiffusionEngine (TextToSpeech.diffusion); diffuser: DiffuserSpec; latents
+    [1, N, D]; conditioning_latents [1, 2C]. Noise comes from torch's generator of the model's device, as in the reference.
+    Returns the denormalised MEL [1, 100, S]."""
+    if latents.shape[0] != 1:
+        raise ValueError("the reference's diffusion sampler is batch-1 (utils/diffusion.py:379)")
+    dev = diffusion_model.dev
+    lat = latents[0].to(dev).float().contiguous()
+    S = lat.shape[0] * 4 * 24000 // 22050
+    iters = diffuser.num_timesteps
+    noise0 = torch.randn(100, S, device=dev) * temperature
+    step_noise = torch.randn(iters, 100, S, device=dev)
+    mel = diffusion_model.sample(lat, conditioning_latents.to(dev).float().reshape(-1), iters, noise0, step_noise,
+                                 cond_free=diffuser.conditioning_free, cond_free_k=diffuser.conditioning_free_k)
+    return mel.unsqueeze(0)
+
+
+def classify_audio_clip(clip):
+    """api.py:133-145 (AudioMiniEncoderWithClassifierHead): not on the synthesis path; out of scope."""
+    raise NotImplementedError("classify_audio_clip is outside the hot path this engine replaces (SURVEY §8f-4)")
+
+
+def pick_best_batch_size_for_gpu():
+    """≙ api.py:148-172 (kept for callers; this engine decodes all candidates in one batch regardless)."""
+    if torch.cuda.is_available():
+        _, available = torch.cuda.mem_get_info()
+        gb = available / (1024 ** 3)
+        if gb > 14:
+            return 16
+        if gb > 10:
+            return 8
+        if gb > 7:
+            return 4
+    return 1
 
 
 class _Tokenizer:
@@ -113,7 +225,36 @@ class TextToSpeech:
         self.clvp = CLVPEngine(state_dicts["clvp"], self.cfg, self.device)
         self.diffusion = DiffusionEngine(state_dicts["diffusion"], self.cfg, self.device)
         self.vocoder = VocoderEngine(state_dicts["vocoder"], self.cfg, self.device)
+        self.conditioning = ConditioningEngine(state_dicts["autoregressive"], state_dicts["diffusion"], self.cfg,
+                                               self.device, mel_norms=state_dicts.get("mel_norms", None)
+                                               if state_dicts.get("mel_norms", None) is not None else _default_mel_norms())
+        self._rlg_sd = (state_dicts.get("rlg_auto"), state_dicts.get("rlg_diffuser"))
+        self.rlg_auto = self.rlg_diffusion = None
         self.last_timings = {}
+
+    def get_conditioning_latents(self, voice_samples, return_mels=False):
+        """≙ api.py:258-299: list of reference clips (22.05 kHz waveforms [1, n]) -> (auto latent [1, D], diffusion latent
+        [1, 2C]) [+ the two stacks of conditioning MELs]."""
+        if not isinstance(voice_samples, (list, tuple)):
+            voice_samples = [voice_samples]
+        with torch.no_grad():
+            if return_mels:
+                auto_latent, auto_conds = self.conditioning.ar_latent(voice_samples, return_mels=True)
+                diffusion_latent, diffusion_conds = self.conditioning.diffusion_latent(voice_samples, return_mels=True)
+                return auto_latent, diffusion_latent, auto_conds, diffusion_conds
+            return self.conditioning.ar_latent(voice_samples), self.conditioning.diffusion_latent(voice_samples)
+
+    def get_random_conditioning_latents(self):
+        """≙ api.py:301-309 (rlg_auto.pth / rlg_diffuser.pth, lazily loaded)."""
+        if self.rlg_auto is None:
+            sa, sd_ = self._rlg_sd
+            if sa is None:
+                sa = torch.load(get_model_path("rlg_auto.pth", self.models_dir), map_location="cpu")
+                sd_ = torch.load(get_model_path("rlg_diffuser.pth", self.models_dir), map_location="cpu")
+            self.rlg_auto = RandomLatentEngine(sa, self.cfg.ar_dim, self.device)
+            self.rlg_diffusion = RandomLatentEngine(sd_, 2 * self.cfg.diff_dim, self.device)
+        with torch.no_grad():
+            return self.rlg_auto(), self.rlg_diffusion()
 
     @property
     def tokenizer(self):
@@ -181,13 +322,14 @@ class TextToSpeech:
         """≙ TextToSpeech.tts (api.py:334-597). `text_tokens` (list of BPE ids) may be given instead of `text`."""
         if cvvp_amount != 0:
             raise NotImplementedError("CVVP is out of scope of this engine (disabled by default in the reference)")
-        if voice_samples is not None:
-            raise NotImplementedError("get_conditioning_latents is a 'next' row (SURVEY §8f-1); pass conditioning_latents")
         if hf_generate_kwargs:
             raise TypeError(f"unsupported generate kwargs: {sorted(hf_generate_kwargs)}")
-        if conditioning_latents is None:
-            raise NotImplementedError("random-voice latents need rlg_*.pth; pass conditioning_latents")
         seed = self.deterministic_state(seed=use_deterministic_seed)
+        # api.py:395-401 (after the seeding, so that the random crop / random voice follow use_deterministic_seed)
+        if voice_samples is not None:
+            conditioning_latents = self.get_conditioning_latents(voice_samples, return_mels=False)
+        elif conditioning_latents is None:
+            conditioning_latents = self.get_random_conditioning_latents()
         dev = self.device
         if text_tokens is None:
             text_tokens = self.tokenizer.encode(text)

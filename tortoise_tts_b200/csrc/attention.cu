@@ -111,6 +111,47 @@ attn_simt_kernel(TtbAttnArgs a) {
   }
 }
 
+// ------------------------------------------------------------------ small general attention (any head_dim = 32 * DPL)
+// One warp per query; lane l holds dims [l*DPL, (l+1)*DPL) of q and of the output row. Used where head_dim != 64 and the
+// sequences are short: the diffusion contextual embedder (C = 2048, 16 heads of 128, T = 101 per clip;
+// models/diffusion_decoder.py:186-192 with QKVAttentionLegacy, arch_util.py:44-77).
+template <int DPL>
+__global__ void __launch_bounds__(128)
+attn_warp_kernel(TtbAttnArgs a) {
+  const int HD = 32 * DPL;
+  const int lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int h = blockIdx.y, seq = blockIdx.z;
+  if (qi >= a.T) return;
+  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(a.qkv) + (long long)seq * a.T * a.ld + h * HD + lane * DPL;
+  float q[DPL], o[DPL];
+#pragma unroll
+  for (int d = 0; d < DPL; ++d) { q[d] = __bfloat162float(base[(long long)qi * a.ld + d]) * a.scale; o[d] = 0.f; }
+  const float* bias = a.bias ? a.bias + (long long)h * (2 * a.T - 1) + (a.T - 1) : nullptr;
+  float m = -INFINITY, l = 0.f;
+  const int kend = a.causal ? qi + 1 : a.T;
+  for (int kj = 0; kj < kend; ++kj) {
+    const __nv_bfloat16* kr = base + (long long)kj * a.ld + a.k_off;
+    const __nv_bfloat16* vr = base + (long long)kj * a.ld + a.v_off;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) s = fmaf(q[d], __bfloat162float(kr[d]), s);
+    s = warp_sum(s);
+    if (bias) s += __ldg(bias + (kj - qi));
+    const float m_new = fmaxf(m, s);
+    const float corr = __expf(m - m_new);
+    const float p = __expf(s - m_new);
+    l = l * corr + p;
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) o[d] = o[d] * corr + p * __bfloat162float(vr[d]);
+    m = m_new;
+  }
+  const float inv = 1.0f / l;
+  __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + ((long long)seq * a.T + qi) * a.ldo + h * HD + lane * DPL;
+#pragma unroll
+  for (int d = 0; d < DPL; ++d) op[d] = __float2bfloat16(o[d] * inv);
+}
+
 // ------------------------------------------------------------------ AR decode attention
 // Single-query attention of every (candidate, head) over [shared prompt prefix | the candidate's own KV] with online
 // softmax (flash-decoding form). grid (H, ceil(B/8)); 8 warps per block, ONE CANDIDATE PER WARP, all on the same head:
@@ -307,6 +348,18 @@ extern "C" int ttb_attention(const TtbAttnArgs* ap, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (a.T <= 0 || a.nseq <= 0) return 0;
   if ((a.ld & 7) || (a.ldo & 7) || (a.k_off & 7) || (a.v_off & 7)) { set_error("ttb_attention: strides must be multiples of 8"); return -1; }
+  if (a.head_dim != 0 && a.head_dim != 64) {
+    if (a.kv || a.lse || a.out_f32) { set_error("ttb_attention: head_dim %d supports the packed form only", a.head_dim); return -1; }
+    dim3 grid((a.T + 3) / 4, a.H, a.nseq);
+    switch (a.head_dim) {
+      case 32: attn_warp_kernel<1><<<grid, 128, 0, st>>>(a); break;
+      case 96: attn_warp_kernel<3><<<grid, 128, 0, st>>>(a); break;
+      case 128: attn_warp_kernel<4><<<grid, 128, 0, st>>>(a); break;
+      default: set_error("ttb_attention: head_dim %d unsupported (32, 64, 96, 128)", a.head_dim); return -1;
+    }
+    TTB_CHECK_LAUNCH("attn_warp_kernel");
+    return 0;
+  }
   if (flash_attention2_supported(a)) return flash_attention2_launch(a, st);
   if (flash_attention_supported(a)) return flash_attention_launch(a, st);
   dim3 grid((a.T + ATT_Q - 1) / ATT_Q, a.H, a.nseq);

@@ -34,7 +34,7 @@ class AttnArgs(C.Structure):
                 ("ld", C.c_int), ("ldo", C.c_int), ("k_off", C.c_int), ("v_off", C.c_int),
                 ("scale", C.c_float), ("causal", C.c_int),
                 ("kv", C.c_void_p), ("kv_v", C.c_void_p), ("kv_headmajor", C.c_int), ("Tk", C.c_int),
-                ("out_f32", C.c_void_p), ("lse", C.c_void_p), ("bias_sat", C.c_int)]
+                ("out_f32", C.c_void_p), ("lse", C.c_void_p), ("bias_sat", C.c_int), ("head_dim", C.c_int)]
 
 
 class DiffStepArgs(C.Structure):
@@ -73,6 +73,7 @@ SYMBOLS = [
     "ttb_transpose_f32", "ttb_cast_pad_bf16", "ttb_broadcast_rows", "ttb_voc_conv1d", "ttb_voc_convt",
     "ttb_voc_lvc_gate", "ttb_voc_to_tokens_bf16", "ttb_debug_gemm_trace",
     "ttb_ar_step_workspace", "ttb_ar_step_setup", "ttb_ar_decode_step", "ttb_ar_step_store_prefix",
+    "ttb_audio_resample", "ttb_audio_stft_mel", "ttb_mean_rows", "ttb_equal_linear",
 ]
 
 
@@ -180,8 +181,9 @@ def groupnorm(x, B, S, Cc, groups, gamma, beta, partials, scale_shift=None, ss_b
                               _stream()), "ttb_groupnorm")
 
 
-def attention(qkv, out, *, nseq, T, H, ld, ldo, k_off, v_off, scale, causal=False, bias=None, bias_sat=0):
+def attention(qkv, out, *, nseq, T, H, ld, ldo, k_off, v_off, scale, causal=False, bias=None, bias_sat=0, head_dim=0):
     a = AttnArgs()
+    a.head_dim = head_dim
     a.bias_sat = int(bias_sat) if bias is not None else 0
     a.qkv, a.out, a.bias = _bf(qkv).data_ptr(), _bf(out).data_ptr(), _p(_f32(bias)).value or 0
     a.nseq, a.T, a.H, a.ld, a.ldo, a.k_off, a.v_off = nseq, T, H, ld, ldo, k_off, v_off
@@ -326,6 +328,28 @@ def cast_pad_bf16(inp, R, Cc, ld_in, out, ldo, ncols_out=None):
 def broadcast_rows(row, R, Cc, out_f32, out_bf16, ldo):
     _chk(load().ttb_broadcast_rows(_p(_f32(row)), R, Cc, _p(_f32(out_f32)), _p(_bf(out_bf16)), ldo, _stream()),
          "ttb_broadcast_rows")
+
+
+def audio_resample(x, n, kernels, down, up, klen, width, out, m):
+    _chk(load().ttb_audio_resample(_p(_f32(x)), n, _p(_f32(kernels)), down, up, klen, width, _p(_f32(out)), m, _stream()),
+         "ttb_audio_resample")
+
+
+def audio_stft_mel(x, n, n_fft, hop, window, twiddle, fb, n_mels, power, clip, floor_v, div, out_bf16=None, ldo=0,
+                   out_f32=None):
+    _chk(load().ttb_audio_stft_mel(_p(_f32(x)), n, n_fft, hop, _p(_f32(window)), _p(_f32(twiddle)), _p(_f32(fb)), n_mels,
+                                   power, 1 if clip else 0, C.c_float(floor_v), _p(_f32(div)), _p(_bf(out_bf16)), ldo,
+                                   _p(_f32(out_f32)), _stream()), "ttb_audio_stft_mel")
+
+
+def mean_rows(x, R, Cc, ld, scale, out, accumulate=False):
+    _chk(load().ttb_mean_rows(_p(_f32(x)), R, Cc, ld, C.c_float(scale), 1 if accumulate else 0, _p(_f32(out)), _stream()),
+         "ttb_mean_rows")
+
+
+def equal_linear(x, K, W, b, N, out, wscale=1.0, bscale=1.0, slope=1.0, gain=1.0):
+    _chk(load().ttb_equal_linear(_p(_f32(x)), K, _p(_f32(W)), _p(_f32(b)), N, C.c_float(wscale), C.c_float(bscale),
+                                 C.c_float(slope), C.c_float(gain), _p(_f32(out)), _stream()), "ttb_equal_linear")
 
 
 def voc_conv1d(x, Cin, L, w, b, Cout, ksize, out, dilation=1, reflect=False, lrelu_in=1.0, lrelu_out=1.0,

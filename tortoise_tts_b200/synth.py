@@ -236,6 +236,8 @@ def synth_all(cfg: ModelConfig, seed=0, suppress_stop=True):
         "diffusion": synth_diffusion(cfg, seed),
         "clvp": synth_clvp(cfg, seed),
         "vocoder": synth_vocoder(cfg, seed),
+        "rlg_auto": synth_rlg(cfg.ar_dim, seed),
+        "rlg_diffuser": synth_rlg(2 * cfg.diff_dim, seed + 1),
     }
 
 
