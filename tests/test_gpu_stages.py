@@ -319,19 +319,52 @@ def test_vocoder_longer(small):
 
 # ----------------------------------------------------------------------------------------------- end to end
 def test_tts_end_to_end_small(small):
-    """tts_with_preset through the drop-in facade on the small checkpoint: shapes / dtype / determinism, and the
-    CLVP ranking + mel of the selected candidate checked stage-wise against the oracle on the SAME codes."""
+    """tts_with_preset through the drop-in facade on the small checkpoint: shapes / dtype / determinism, AND the
+    north-star parity target: CLVP scores of every candidate and the mel of the selected candidate against the oracle
+    run on the SAME codes / latents / injected noise (stage-wise, so that sampling differences cannot hide behind it)."""
     from tortoise_tts_b200.api import TextToSpeech
+    from oracle import ar as oar, clvp as oclvp, diffusion as od
     cfg, sds, g = small
     tts = TextToSpeech(state_dicts=sds, config=cfg, kv_cache=True)
     cl = (torch.randn(1, cfg.ar_dim), torch.randn(1, 2 * cfg.diff_dim) * 0.3)
     kw = dict(text_tokens=TEXT[:-1], conditioning_latents=cl, use_deterministic_seed=5, max_mel_tokens=24,
               num_autoregressive_samples=8, diffusion_iterations=4, verbose=False)
+    tts.debug_capture = True
     a = tts.tts_with_preset("unused", preset="ultra_fast", **kw)
+    dbg = tts.last_debug
+    tts.debug_capture = False
     b = tts.tts_with_preset("unused", preset="ultra_fast", **kw)
     assert a.dtype == torch.float32 and a.device.type == "cpu" and a.dim() == 3 and a.shape[:2] == (1, 1)
     assert a.shape[-1] % 256 == 0 and a.abs().max().item() <= 1.0
     assert torch.equal(a, b)
+    # ---- stage-wise parity on the codes this call produced
+    toks = TEXT[:-1] + [0]
+    codes = dbg["codes"].cpu().long()
+    with torch.no_grad():
+        want_scores = oclvp.scores(sds["clvp"], cfg, torch.tensor(toks), codes)
+    e = (dbg["scores"].cpu() - want_scores).abs().max().item()
+    report("e2e small CLVP scores abs", e)
+    assert e < 0.03
+    j = 0
+    best = int(dbg["best"][j])
+    assert best == int(torch.argmax(dbg["scores"]))
+    with torch.no_grad():
+        lat_full = oar.latents(sds["autoregressive"], cfg, cl[0], toks, codes[best:best + 1])
+    n_lat = dbg["latents"][j].shape[0]
+    assert n_lat == oar.calm_trim_length(codes[best])
+    r = _rel(dbg["latents"][j].cpu(), lat_full[0, :n_lat])
+    report("e2e small latents of the selected candidate", r)
+    assert r < 0.03
+    noise0, step_noise = (t.cpu() for t in dbg["noise"][j])
+    with torch.no_grad():
+        want_mel = od.spectrogram_diffusion(sds["diffusion"], cfg, lat_full[:, :n_lat], cl[1], noise0.unsqueeze(0),
+                                            step_noise.unsqueeze(1), 4, cond_free=False)[0]
+    got_mel = dbg["mel"][j].cpu()
+    err = (got_mel - want_mel).abs().max().item()
+    rms = (got_mel - want_mel).pow(2).mean().sqrt().item()
+    report("e2e small mel max (range 13.8)", err)
+    report("e2e small mel rms", rms)
+    assert err < 1.5 and rms < 0.3          # same bound as the sampled-mel stage test (DESIGN §2)
     outs = tts.tts_with_preset("unused", preset="ultra_fast", k=2, **kw)
     assert isinstance(outs, list) and len(outs) == 2
     with pytest.raises(KeyError):

@@ -231,6 +231,8 @@ class TextToSpeech:
         self._rlg_sd = (state_dicts.get("rlg_auto"), state_dicts.get("rlg_diffuser"))
         self.rlg_auto = self.rlg_diffusion = None
         self.last_timings = {}
+        self.debug_capture = False
+        self.last_debug = None
 
     def get_conditioning_latents(self, voice_samples, return_mels=False):
         """≙ api.py:258-299: list of reference clips (22.05 kHz waveforms [1, n]) -> (auto latent [1, D], diffusion latent
@@ -361,6 +363,9 @@ class TextToSpeech:
             scores, codes = parallel.gather_candidates(scores, codes, B)
             best = torch.topk(scores, k=k).indices
             best_codes = codes[best].contiguous()
+            if self.debug_capture:      # parity hook (tests): the intermediate results of the stages of this call
+                self.last_debug = {"seed": seed, "codes": codes.clone(), "scores": scores.clone(), "best": best.clone(),
+                                   "latents": {}, "mel": {}, "noise": {}}
             ev[2].record()
             # rendering plan: candidate j -> owner rank (+ the rank pair sharing its CFG denoiser when ws >= 2)
             use_pair = cond_free and ws >= 2 and os.environ.get("TTB_CFG_PAIR", "1") == "1"   # TTB_CFG_PAIR=0 disables
@@ -389,6 +394,10 @@ class TextToSpeech:
                 mel = self.diffusion.sample(lat, diff_cond, diffusion_iterations, noise0, step_noise, cond_free=cond_free,
                                             cond_free_k=cond_free_k, pair=pair)
                 e[2].record()
+                if self.debug_capture:
+                    self.last_debug["latents"][j] = lat.clone()
+                    self.last_debug["mel"][j] = mel.clone()
+                    self.last_debug["noise"][j] = (noise0.clone(), step_noise.clone())
                 if owner == rank:
                     # the reference draws the vocoder noise on the CPU (vocoder.py:307); device draw here
                     z = torch.randn(64, S + 10, generator=gj, device=dev)
