@@ -23,12 +23,16 @@ if ROOT not in sys.path:
 
 METRIC = "audio-seconds/sec at preset='standard'"
 UNIT = "audio-s/s"
-# ncu --set full, one launch each at the bench shapes (profiles/ncu_r01/*.ncu-rep): DRAM bytes read + written
-NCU_TRAFFIC_BYTES = {
-    "AR decode attention": 228.770560e6 + 8.168192e6,      # candidate KV stream kernel, ctx 174+215 (225.4 MB algorithmic)
-    "diffusion attention": 23.328768e6,                    # qkv 23.0 MB read once; output stays in L2
-    "diffusion conv k=3 GEMM": 29.341696e6 + 6.656e3,      # A 7.7 + W 6.3 + residual 15.3 MB; output stays in L2
-}
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the probed kernels, parsed from the committed ncu
+    --set full captures by tools/ncu_traffic.py into profiles/ncu_traffic.json ({probe-name prefix: {bytes, source}})."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return {}
+    with open(p) as f:
+        return json.load(f)
 
 
 def load_tokens(name="para53"):
@@ -83,7 +87,7 @@ def peaks():
     return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
-def kernel_probes(tts, cfg, n_mel, B, P):
+def kernel_probes(tts, cfg, n_mel, B, P, iters=200):
     """Times the candidate dominant kernels live, in isolation at the workload's shapes, with CUDA events on the
     launching stream; returns per-kernel dicts with achieved throughput against the roofline that bounds each."""
     import torch
@@ -119,7 +123,7 @@ def kernel_probes(tts, cfg, n_mel, B, P):
     ms = timeit(lambda: lib.attention(qkv, o, nseq=2, T=S, H=H, ld=3 * C, ldo=C, k_off=C, v_off=2 * C, scale=0.125, bias=bias,
                                       bias_sat=64), flush=flush)
     flops = 2 * H * 4.0 * S * S * 64
-    out.append(dict(kernel="diffusion attention (2x16 heads, S=%d)" % S, bound="tensor", ms=ms, count=13 * 200,
+    out.append(dict(kernel="diffusion attention (2x16 heads, S=%d)" % S, bound="tensor", ms=ms, count=13 * iters,
                     achieved=flops / ms / 1e9, peak=tfl, unit="TFLOP/s"))
     # (2) diffusion conv k=3 as GEMM: [2, S, 1024] x [1024, 3*1024]
     a = torch.randn(2, S, C, device=dev).to(torch.bfloat16)
@@ -130,29 +134,59 @@ def kernel_probes(tts, cfg, n_mel, B, P):
                                  res_bstride=S * C, outf_bstride=S * C), flush=flush)
     flops = 2 * 2.0 * S * C * 3 * C
     out.append(dict(kernel="diffusion conv k=3 GEMM (tcgen05, M=2x%d N=1024 K=3072)" % S, bound="tensor", ms=ms,
-                    count=16 * 200, achieved=flops / ms / 1e9, peak=tfl, unit="TFLOP/s"))
-    # (3) AR decode attention at the mean context (step n_mel/2): KV stream of all candidates, one layer
-    Hh = cfg.ar_heads
-    D = cfg.ar_dim
-    Nmax = n_mel
-    ck = torch.zeros(B, Hh, Nmax, 64, device=dev, dtype=torch.bfloat16)
-    cv = torch.zeros_like(ck)
-    pk = torch.zeros(Hh, P, 64, device=dev, dtype=torch.bfloat16)
-    pv = torch.zeros_like(pk)
-    qkv2 = torch.randn(B, 3 * D, device=dev).to(torch.bfloat16)
-    o2 = torch.empty(B, D, device=dev, dtype=torch.bfloat16)
-    state = torch.zeros(64, dtype=torch.int32, device=dev)
-    state[0] = n_mel // 2
-    so = torch.zeros(2, B, D, device=dev)
-    sl = torch.zeros(2, B, Hh, device=dev)
-    ms = timeit(lambda: lib.ar_decode_attention(qkv2, pk, pv, ck, cv, state, B, Hh, P, Nmax, o2, so, sl), flush=flush)
-    nbytes = B * Hh * (n_mel // 2) * 64 * 2 * 2 + Hh * P * 64 * 2 * 2   # candidate K+V (bf16) + shared prefix once
-    out.append(dict(kernel="AR decode attention (B=%d, ctx=%d+%d)" % (B, P, n_mel // 2), bound="hbm", ms=ms,
-                    count=30 * (n_mel - 1), achieved=nbytes / ms / 1e6, peak=hbm, unit="GB/s"))
+                    count=16 * iters, achieved=flops / ms / 1e9, peak=tfl, unit="TFLOP/s"))
+    # (3) the AR decode step at the mean context (step n_mel/2): ONE kernel = all 30 layers + mel_head for every candidate
+    # of this GPU. Algorithmic bytes per launch: every weight once (bf16) + the shared prompt K/V once per layer
+    # + every candidate's own K/V (bf16) of the n_mel/2 positions decoded so far.
+    eng = tts.autoregressive
+    st = eng._decode_state(B, P, n_mel)
+    Hh, D, L = cfg.ar_heads, cfg.ar_dim, cfg.ar_layers
+    if st["fused"]:
+        hd = eng._step_handle(st, 1)
+        st["state"].zero_()
+        st["state"][0] = n_mel // 2
+        st["codes"].zero_()
+        ms = timeit(lambda: hd.step(), flush=flush)
+        assert int(st["state"][2].item()) == 0, "ar_step_kernel timed out internally"
+        w_bytes = (L * 12 * D * D + cfg.number_mel_codes * D) * 2
+        kv_bytes = L * Hh * P * 128 * 2 + B * L * Hh * (n_mel // 2) * 128 * 2
+        out.append(dict(kernel="AR decode step kernel (B=%d, ctx=%d+%d, 30 layers + mel_head)" % (B, P, n_mel // 2),
+                        bound="hbm", ms=ms, count=n_mel - 1, achieved=(w_bytes + kv_bytes) / ms / 1e6, peak=hbm, unit="GB/s",
+                        algorithmic_bytes=w_bytes + kv_bytes))
+        # the attention phase of one layer alone (same kernel, phase mask): the KV stream against the HBM roofline
+        ms_a = timeit(lambda: hd.step(phase_mask=4, layer_begin=L // 2, layer_end=L // 2 + 1), flush=flush)
+        nbytes = B * Hh * (n_mel // 2) * 128 * 2 + Hh * P * 128 * 2
+        out.append(dict(kernel="AR decode attention phase (1 layer, B=%d, ctx=%d+%d)" % (B, P, n_mel // 2), bound="hbm",
+                        ms=ms_a, count=0, achieved=nbytes / ms_a / 1e6, peak=hbm, unit="GB/s", algorithmic_bytes=nbytes))
+    else:
+        ck = torch.zeros(B, Hh, n_mel, 64, device=dev, dtype=torch.bfloat16)
+        cv = torch.zeros_like(ck)
+        pk = torch.zeros(Hh, P, 64, device=dev, dtype=torch.bfloat16)
+        pv = torch.zeros_like(pk)
+        qkv2 = torch.randn(B, 3 * D, device=dev).to(torch.bfloat16)
+        o2 = torch.empty(B, D, device=dev, dtype=torch.bfloat16)
+        state = torch.zeros(64, dtype=torch.int32, device=dev)
+        state[0] = n_mel // 2
+        so = torch.zeros(2, B, D, device=dev)
+        sl = torch.zeros(2, B, Hh, device=dev)
+        ms = timeit(lambda: lib.ar_decode_attention(qkv2, pk, pv, ck, cv, state, B, Hh, P, n_mel, o2, so, sl), flush=flush)
+        nbytes = B * Hh * (n_mel // 2) * 64 * 2 * 2 + Hh * P * 64 * 2 * 2
+        out.append(dict(kernel="AR decode attention (B=%d, ctx=%d+%d)" % (B, P, n_mel // 2), bound="hbm", ms=ms,
+                        count=30 * (n_mel - 1), achieved=nbytes / ms / 1e6, peak=hbm, unit="GB/s", algorithmic_bytes=nbytes))
     for d in out:
         d["frac"] = d["achieved"] / d["peak"]
         d["total_ms_per_utterance"] = d["ms"] * d["count"]
     return out, how
+
+
+def config5_tokens(base):
+    """BASELINE configs[4]: 8 long utterances. Token lists of growing length built by cycling the 169-token paragraph
+    (T = 169 ... 337; SURVEY quotes T up to ~380, capped here so that the prompt fits the one-kernel decode step)."""
+    return [[base[i % len(base)] for i in range(n)] for n in (169, 193, 217, 241, 265, 289, 313, 337)]
+
+
+ITERS = {"standard": 200, "fast": 80, "ultra_fast": 30, "high_quality": 400}
+NCAND = {"standard": 256, "high_quality": 256, "fast": 96, "ultra_fast": 16}
 
 
 def run_engine(args):
@@ -164,7 +198,7 @@ def run_engine(args):
     torch.cuda.set_device(local)
     if world > 1:
         import datetime
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=300))
     import __graft_entry__ as ge
     if rank == 0:
         ge.build()
@@ -181,16 +215,23 @@ def run_engine(args):
     tts = TextToSpeech(state_dicts=sds, config=cfg, kv_cache=True, device="cuda:%d" % local)
     progress("engines ready")
     tokens = load_tokens(args.text)
-    n_mel = args.mel_tokens
+    config5 = args.workload == "config5"
+    preset = "high_quality" if config5 else args.preset
+    n_mel = 500 if config5 else args.mel_tokens
     g = torch.Generator().manual_seed(0)
     cl_host = ((torch.randn(1, cfg.ar_dim, generator=g) * 0.5).pin_memory(),
                (torch.randn(1, 2 * cfg.diff_dim, generator=g) * 0.3).pin_memory())
-    kw = dict(text_tokens=tokens, conditioning_latents=cl_host, max_mel_tokens=n_mel, verbose=False, k=1)
+    kw = dict(conditioning_latents=cl_host, max_mel_tokens=n_mel, verbose=False, k=1)
     if args.preset_override:
         kw.update(json.loads(args.preset_override))
+    utt = config5_tokens(tokens) if config5 else [tokens]
 
     def step(i):
-        return tts.tts_with_preset("", preset=args.preset, use_deterministic_seed=1000 + i, **kw)
+        if config5:
+            # read.py loop: 8 utterances, one whole utterance per GPU (no collective inside an utterance)
+            return tts.tts_long("|".join("u%d" % u for u in range(len(utt))), preset=preset, text_tokens_list=utt,
+                                use_deterministic_seed=1000 + i, **kw)
+        return tts.tts_with_preset("", preset=preset, text_tokens=tokens, use_deterministic_seed=1000 + i, **kw)
 
     def sync():
         if world > 1:
@@ -207,9 +248,15 @@ def run_engine(args):
     dev_ms = []
     stage = {}
     t0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(args.steps):
+        ev0.record()
         wav = step(args.warmup + i)
-        dev_ms.append(tts.last_timings["device_total_ms"])
+        ev1.record()
+        torch.cuda.synchronize()
+        # device time of the step: CUDA events on the launching stream around the whole call (config5: the sum of this
+        # rank's utterances); for one utterance this equals the stage events inside tts()
+        dev_ms.append(ev0.elapsed_time(ev1) if config5 else tts.last_timings["device_total_ms"])
         progress("timed step %d: %.1f ms on device" % (i, dev_ms[-1]))
         for k_, v in tts.last_timings.items():
             stage[k_] = stage.get(k_, 0.0) + v / args.steps
@@ -228,82 +275,113 @@ def run_engine(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    B = 256 if args.preset in ("standard", "high_quality") else (96 if args.preset == "fast" else 16)
-    h2d = sum(t.numel() * 4 for t in cl_host) + 4 * (len(tokens) + 1)
+    B = NCAND[preset]
+    iters = ITERS[preset]
+    h2d = sum(t.numel() * 4 for t in cl_host) * len(utt) + sum(4 * (len(u) + 1) for u in utt)
+    if config5:
+        workload = ("configs[4]: preset='high_quality' (256 AR samples, 400 diffusion iters), 8 utterances of %s BPE tokens, "
+                    "N=%d mel tokens each -> %.1f s audio, k=1" % ("/".join(str(len(u)) for u in utt), n_mel, audio_s))
+        par = "whole utterances sharded %d/GPU (read.py loop), no collective inside an utterance" % ((len(utt) + world - 1) // world)
+    else:
+        workload = ("configs[2]: preset='%s' (%d AR samples, %d diffusion iters), %d-token paragraph, N=%d mel tokens -> "
+                    "%.2f s audio, k=1" % (preset, B, iters, len(tokens), n_mel, audio_s))
+        par = "candidates sharded %d/GPU; CFG branch pair on 2 GPUs for the k=1 diffusion tail" % ((B + world - 1) // world)
     line = {
-        "metric": METRIC, "value": audio_s / (dev_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC if not config5 else "audio-seconds/sec at preset='high_quality' (8 utterances)",
+        "value": audio_s / (dev_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16 tensor-core operands, fp32 accumulate/residual/norm/softmax/scheduler",
         "data": "synthetic (seeded random checkpoint in the reference .pth layout, EOS suppressed; synthetic latents)",
-        "config": {"workload": "configs[2]: preset='%s' (%d AR samples, %d diffusion iters), %d-token paragraph, "
-                               "N=%d mel tokens -> %.2f s audio, k=1" % (args.preset, B, {"standard": 200, "fast": 80,
-                                                                         "ultra_fast": 30, "high_quality": 400}[args.preset],
-                                                                         len(tokens), n_mel, audio_s),
+        "config": {"workload": workload,
                    "l2": "working set (1.9 GB weights + %.1f GB KV cache) >> 126 MB L2; no flush between steps" %
-                         (2 * 30 * B * 16 * n_mel * 64 * 2 / 1e9),
-                   "parallelism": "candidates sharded %d/GPU" % ((B + world - 1) // world)},
+                         (2 * 30 * ((B + world - 1) // world if not config5 else B) * 16 * n_mel * 64 * 2 / 1e9),
+                   "parallelism": par},
         "e2e": {"value": audio_s / (ms_per_step / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": int(wav.numel() * 4)},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "stage_ms": {k_: round(v, 2) for k_, v in stage.items()},
     }
-    if world == 1:
+    if not config5:
+        # the two phases scale differently: candidates shard over all GPUs, the k=1 tail over a pair
+        line["phase_ms"] = {"candidate_sharded (ar+clvp)": round(stage.get("ar_ms", 0) + stage.get("clvp_ms", 0), 2),
+                            "tail (latents+diffusion+vocoder)": round(stage.get("latents_ms", 0) + stage.get("diffusion_ms", 0)
+                                                                      + stage.get("vocoder_ms", 0), 2)}
+    if world == 1 and not config5:
         progress("kernel probes")
-        probes, how = kernel_probes(tts, cfg, n_mel, B, len(tokens) + 5)
+        probes, how = kernel_probes(tts, cfg, n_mel, B, len(tokens) + 5, iters)
         progress("probes done")
         dom = max(probes, key=lambda d: d["total_ms_per_utterance"])
-        # dram__bytes_read + dram__bytes_write per launch of the dominant kernel from the committed ncu --set full
-        # captures (profiles/ncu_summary_r01_run10.txt, same shapes as the probes); null for a kernel without a capture
-        traffic = None
-        for key, val in NCU_TRAFFIC_BYTES.items():
+        traffic, source = None, None
+        for key, val in ncu_traffic().items():
             if dom["kernel"].startswith(key):
-                traffic = val
+                traffic, source = val["bytes"], val["source"]
         line["roofline"] = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": round(dom["achieved"], 2),
                             "peak": dom["peak"], "unit": dom["unit"], "frac": round(dom["frac"], 4), "traffic": traffic,
-                            "traffic_source": "profiles/ncu_summary_r01_run10.txt" if traffic else None,
-                            "peak_source": how, "launch_ms": round(dom["ms"], 4)}
+                            "traffic_source": source, "peak_source": how, "launch_ms": round(dom["ms"], 4),
+                            "algorithmic": dom.get("algorithmic_bytes")}
         line["kernels"] = [{k_: (round(v, 4) if isinstance(v, float) else v) for k_, v in d.items()} for d in probes]
         if not args.no_cpu_baseline:
-            progress("cpu baseline (oracle port on the host cores)")
-            line["cpu_baseline"] = cpu_baseline(cfg, sds, tokens, B, n_mel, args)
+            progress("cpu baseline (reference modules on the host cores)")
+            line["cpu_baseline"] = cpu_baseline(args, "cpu")
             progress("cpu baseline done")
+        if not args.no_ref_gpu:
+            progress("reference in PyTorch eager on this GPU (BASELINE.md: bar to beat)")
+            line["reference_gpu"] = cpu_baseline(args, "cuda")
+            progress("reference-on-GPU done")
     print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(cfg, sds, tokens, B, n_mel, args):
-    # child process under a timeout: the oracle's thread pool must not inherit this process's CUDA-side state, and a
+def _ref_available():
+    from oracle.ref_shims import reference_available
+    return reference_available()
+
+
+def _baseline_cmd(args, device, repeat=1):
+    """The unmodified reference modules when they are importable (oracle/_ref or /root/reference), else the oracle port."""
+    mod = "oracle.ref_baseline" if _ref_available() else "oracle.cpu_baseline"
+    cmd = [sys.executable, "-m", mod, "--preset", args.preset, "--mel-tokens", str(args.mel_tokens),
+           "--tokens-json", os.path.join(ROOT, "tests", "golden", "bench_text_tokens.json"), "--text", args.text,
+           "--repeat", str(repeat)]
+    if mod == "oracle.ref_baseline":
+        cmd += ["--device", device]
+    elif device != "cpu":
+        return None
+    return cmd
+
+
+def cpu_baseline(args, device):
+    # child process under a timeout: the baseline's thread pool must not inherit this process's CUDA-side state, and a
     # host whose CPU quota misbehaves must not take the GPU arm's JSON line down with it
-    cmd = [sys.executable, "-m", "oracle.cpu_baseline", "--preset", args.preset, "--mel-tokens", str(n_mel),
-           "--tokens-json", os.path.join(ROOT, "tests", "golden", "bench_text_tokens.json"), "--text", args.text]
+    cmd = _baseline_cmd(args, device)
+    if cmd is None:
+        return {"value": None, "unit": UNIT, "kind": "port", "sample": "the oracle port has no %s mode" % device}
     try:
         out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=args.cpu_timeout)
         r = json.loads(out.stdout.strip().splitlines()[-1])
     except subprocess.TimeoutExpired:
-        return {"value": None, "unit": UNIT, "cores": None, "kind": "port",
+        return {"value": None, "unit": UNIT, "cores": None, "kind": "reference" if _ref_available() else "port",
                 "sample": "not finished within %d s on this host" % args.cpu_timeout}
     except (ValueError, IndexError):
         return {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": "failed: " + out.stderr[-300:]}
-    return {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+    return {"value": r["value"], "unit": UNIT, "cores": r["cores"], "cores_available": r.get("cores_available"),
+            "kind": r.get("kind", "port"), "device": r.get("device", "cpu"), "sample": r["sample"],
             "total_s_extrapolated": round(r["total_s"], 1), "units_s": {k: round(v, 4) for k, v in r["units"].items()}}
 
 
 def run_reference(args):
-    """The reference arm: the reference's own CPU implementation of the path is Python/PyTorch and does not travel to
-    the GPU box, so its restatement (oracle/, pinned against the reference modules) is timed on the host cores."""
+    """The reference arm: the reference's own implementation of the path (its unmodified PyTorch modules, copied next to
+    the oracle by oracle/build_ref.py; the oracle port only if that copy is missing) timed on the host cores - or, with
+    --device cuda, in PyTorch eager on the GPU."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     tokens = load_tokens(args.text)
     n = args.warmup + args.steps
-    # one child process takes all W+K samples (checkpoint synthesis and the thread-count probe are paid once); each
-    # sample is the bounded unit-cost measurement of oracle/cpu_baseline.py (~20-40 s of CPU work)
-    cmd = [sys.executable, "-m", "oracle.cpu_baseline", "--preset", args.preset, "--mel-tokens", str(args.mel_tokens),
-           "--tokens-json", os.path.join(ROOT, "tests", "golden", "bench_text_tokens.json"), "--text", args.text,
-           "--repeat", str(n)]
+    cmd = _baseline_cmd(args, args.device, repeat=n)
     t0 = time.perf_counter()
     samples = []
     try:
@@ -320,7 +398,7 @@ def run_reference(args):
     wall = time.perf_counter() - t0
     timed = samples[args.warmup:] if len(samples) > args.warmup else samples[-1:]
     if not timed:
-        print(json.dumps({"impl": "reference", "unavailable": "CPU oracle produced no sample: " + err[-200:].replace("\n", " ")}))
+        print(json.dumps({"impl": "reference", "unavailable": "reference produced no sample: " + err[-200:].replace("\n", " ")}))
         return
     last = timed[-1]
     v = sum(s["value"] for s in timed) / len(timed)
@@ -328,9 +406,12 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": audio_s / v * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[2]: preset='%s', %d-token paragraph, N=%d mel tokens (CPU oracle port of the "
-                                   "reference path, unit costs extrapolated)" % (args.preset, len(tokens), args.mel_tokens)},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+            "config": {"workload": "configs[2]: preset='%s', %d-token paragraph, N=%d mel tokens (%s on %s, unit costs "
+                                   "extrapolated)" % (args.preset, len(tokens), args.mel_tokens,
+                                                      "unmodified reference modules" if last.get("kind") == "reference"
+                                                      else "CPU oracle port of the reference path", last.get("device", "cpu"))},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "cores_available": last.get("cores_available"),
+                             "kind": last.get("kind", "port"), "sample": last["sample"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "bench_wall_s": round(wall, 1)}
     print(json.dumps(line))
@@ -342,12 +423,17 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--workload", default="config3", choices=["config3", "config5"],
+                    help="config3 = BASELINE configs[2] (the metric's configuration; configs[3] under torchrun); config5 = "
+                         "configs[4]: high_quality, 8 utterances, one per GPU")
+    ap.add_argument("--device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: where the reference runs")
     ap.add_argument("--preset", default="standard")
     ap.add_argument("--text", default="para53")
     ap.add_argument("--mel-tokens", type=int, default=430)
     ap.add_argument("--preset-override", default=None, help="JSON dict of tts kwargs (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-timeout", type=int, default=240, help="seconds allowed per CPU-oracle sample")
+    ap.add_argument("--no-ref-gpu", action="store_true")
+    ap.add_argument("--cpu-timeout", type=int, default=240, help="seconds allowed per baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

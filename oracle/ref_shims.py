@@ -12,7 +12,10 @@ import os
 import sys
 import types
 
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")    # oracle/build_ref.py (git-ignored copy)
 REFERENCE_ROOT = os.environ.get("TORTOISE_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "tortoise")) and os.path.isdir(os.path.join(_VENDORED, "tortoise")):
+    REFERENCE_ROOT = _VENDORED                # GPU box: the unmodified reference package as copied by the build recipe
 
 
 def reference_available() -> bool:
