@@ -141,6 +141,7 @@ def kernel_probes(tts, cfg, n_mel, B, P, iters=200):
     eng = tts.autoregressive
     st = eng._decode_state(B, P, n_mel)
     Hh, D, L = cfg.ar_heads, cfg.ar_dim, cfg.ar_layers
+    mode = st["mode"]
     if st["fused"]:
         hd = eng._step_handle(st, 1)
         st["state"].zero_()
@@ -151,13 +152,14 @@ def kernel_probes(tts, cfg, n_mel, B, P, iters=200):
         w_bytes = (L * 12 * D * D + cfg.number_mel_codes * D) * 2
         kv_bytes = L * Hh * P * 128 * 2 + B * L * Hh * (n_mel // 2) * 128 * 2
         out.append(dict(kernel="AR decode step kernel (B=%d, ctx=%d+%d, 30 layers + mel_head)" % (B, P, n_mel // 2),
-                        bound="hbm", ms=ms, count=n_mel - 1, achieved=(w_bytes + kv_bytes) / ms / 1e6, peak=hbm, unit="GB/s",
-                        algorithmic_bytes=w_bytes + kv_bytes))
+                        bound="hbm", ms=ms, count=(n_mel - 1) if mode == "fused" else 0,
+                        achieved=(w_bytes + kv_bytes) / ms / 1e6, peak=hbm, unit="GB/s", algorithmic_bytes=w_bytes + kv_bytes))
         # the attention phase of one layer alone (same kernel, phase mask): the KV stream against the HBM roofline
         ms_a = timeit(lambda: hd.step(phase_mask=4, layer_begin=L // 2, layer_end=L // 2 + 1), flush=flush)
         nbytes = B * Hh * (n_mel // 2) * 128 * 2 + Hh * P * 128 * 2
-        out.append(dict(kernel="AR decode attention phase (1 layer, B=%d, ctx=%d+%d)" % (B, P, n_mel // 2), bound="hbm",
-                        ms=ms_a, count=0, achieved=nbytes / ms_a / 1e6, peak=hbm, unit="GB/s", algorithmic_bytes=nbytes))
+        out.append(dict(kernel="AR decode attention kernel (ar_step_kernel, attention phase of 1 layer, B=%d, ctx=%d+%d)" %
+                        (B, P, n_mel // 2), bound="hbm", ms=ms_a, count=L * (n_mel - 1) if mode == "mixed" else 0,
+                        achieved=nbytes / ms_a / 1e6, peak=hbm, unit="GB/s", algorithmic_bytes=nbytes))
     else:
         ck = torch.zeros(B, Hh, n_mel, 64, device=dev, dtype=torch.bfloat16)
         cv = torch.zeros_like(ck)

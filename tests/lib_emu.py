@@ -171,10 +171,23 @@ class ArStep:
     def step(self, phase_mask=0, layer_begin=0, layer_end=0):
         k = self.kw
         B, D, H, L, V, P, Nmax = k["B"], k["D"], k["H"], k["L"], k["V"], k["P"], k["Nmax"]
-        assert phase_mask == 0 and layer_end == 0, "the emulation runs whole steps only"
         st = k["state"]
         j = int(st[0])
         slot = j - 1
+        if phase_mask == 4:          # attention phase of one layer (the "mixed" mode of AREngine)
+            assert layer_end == layer_begin + 1
+            l = layer_begin
+            pkv = k["prefix_kv"].view(L, H, P, 2, 64)
+            ckv = k["cand_kv"].view(L, B, H, Nmax, 2, 64)
+            qkv = k["qkv"].view(B, 3 * D)
+            ckv[l, :, :, slot, 0] = qkv[:, D:2 * D].reshape(B, H, 64)
+            ckv[l, :, :, slot, 1] = qkv[:, 2 * D:].reshape(B, H, 64)
+            q = qkv[:, :D].reshape(B, H, 1, 64).float() * 0.125
+            Kc = torch.cat([pkv[l, :, :, 0].float().unsqueeze(0).expand(B, -1, -1, -1), ckv[l, :, :, :slot + 1, 0].float()], 2)
+            Vc = torch.cat([pkv[l, :, :, 1].float().unsqueeze(0).expand(B, -1, -1, -1), ckv[l, :, :, :slot + 1, 1].float()], 2)
+            k["o"].view(B, D).copy_((torch.softmax(q @ Kc.transpose(-1, -2), -1) @ Vc).reshape(B, D).to(torch.bfloat16))
+            return
+        assert phase_mask == 0 and layer_end == 0, "the emulation runs whole steps or one attention phase"
         tok = k["codes"].view(B, k["ld_codes"])[:, j - 1].long()
         x = k["mel_emb"][tok] + k["mel_pos"][j + 1 if k["pos_mode"] else j]
 

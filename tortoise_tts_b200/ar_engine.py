@@ -61,6 +61,14 @@ class AREngine:
     # TTB_AR_FUSED=1 (default): the decode step is ONE persistent kernel (csrc/ar_step.cu) + the sampler; 0 = the round-1
     # per-op CUDA graph (kept as the A/B baseline and for shapes the fused kernel does not cover)
     FUSED = int(_os.environ.get("TTB_AR_FUSED", "1"))
+    # How the step runs when the one-kernel form is available (measured on B200, tools/ar_step_probe.py, step time at
+    # context 174+215): "fused" = everything in the persistent kernel: 1.85 ms at 32 candidates (per-op graph: 2.28), but
+    # its phases grow with the batch (2.8 / 3.7 / 4.1 ms at 64 / 128 / 256 against 2.2 / 2.4 / 3.1): one CTA per SM
+    # serialises TMA wait -> MMA -> epilogue inside a phase, which several small kernels per SM overlap. "mixed" = the
+    # per-op graph with its three attention kernels (prefix flash + candidate stream + merge, 65 us at 256 candidates)
+    # replaced by the persistent kernel's attention phase (one launch, 54 us). "auto" picks by batch size.
+    MODE = _os.environ.get("TTB_AR_MODE", "auto")            # auto | fused | mixed | perop
+    FUSED_MAX_B = int(_os.environ.get("TTB_AR_FUSED_MAX_B", "40"))
     SPLITK_PROJ = 2     # attn.c_proj  (K = D):   32 n-tiles x 2 m-tiles x 2 splits = 128 CTAs at D=1024, B=256
     SPLITK_PROJ2 = 4    # mlp.c_proj   (K = 4D):  32 x 2 x 4 = 256 CTAs
 
@@ -132,7 +140,12 @@ class AREngine:
         st = dict(key=key, P=P, B=B, Nmax=Nmax)
         st["px"] = torch.empty(P, D, dtype=torch.float32, device=dev)
         st["pws"] = self._alloc_trunk(P)
-        st["fused"] = bool(self.FUSED) and lib.ar_step_supported(B, D, H, P)
+        ok = bool(self.FUSED) and lib.ar_step_supported(B, D, H, P)
+        mode = self.MODE if ok else "perop"
+        if mode == "auto":
+            mode = "fused" if B <= self.FUSED_MAX_B else "mixed"
+        st["mode"] = mode
+        st["fused"] = mode in ("fused", "mixed")           # interleaved K|V cache layout (csrc/ar_step.cu)
         if st["fused"]:
             # K and V of a position adjacent: one (candidate, head) stream is one contiguous byte range (csrc/ar_step.cu)
             st["pkv"] = torch.empty(L, H, P, 2, 64, dtype=torch.bfloat16, device=dev)
@@ -178,12 +191,13 @@ class AREngine:
         """One trunk pass for the last sampled token of every candidate + fused sampling of the next one."""
         B, P, Nmax, D, H = st["B"], st["P"], st["Nmax"], self.D, self.H
         x, ws = st["x"], st["ws"]
-        if st["fused"]:
+        if st["mode"] == "fused":
             self._step_handle(st, sp["pos_mode"]).step()
             lib.ar_sample(st["logits"], self.V, self.V, B, st["uniforms"], Nmax, st["seen"], st["codes"], Nmax,
                           st["finished"], st["state"], sp["temperature"], sp["top_k"], sp["top_p"], sp["rep_penalty"],
                           self.cfg.stop_mel_token, advance=True)
             return
+        hd = self._step_handle(st, sp["pos_mode"]) if st["mode"] == "mixed" else None
         lib.ar_embed_step(st["codes"], Nmax, st["state"], self.w.mel_emb, self.w.mel_pos, B, D, sp["pos_mode"], x)
         # Skinny-M decode (M = B candidates): every GEMM is weight-streaming bound, so the grid is widened with
         # 32-column tiles and, for the two GEMMs that feed the residual stream, split-K; their partial sums, bias and
@@ -202,8 +216,11 @@ class AREngine:
             else:
                 lib.residual_layernorm(x, B, D, prev[0], prev[1], B * D, prev[2], lw["ln1_g"], lw["ln1_b"], out_bf16=ws["a"])
             lib.gemm(ws["a"], lw["wqkv"], M=B, N=3 * D, K=D, bias=lw["bqkv"], out_bf16=ws["qkv"], cluster=cl, **wide)
-            lib.ar_decode_attention(ws["qkv"], st["pk"][l], st["pv"][l], st["ck"][l], st["cv"][l], st["state"], B, H, P,
-                                    Nmax, ws["o"], st["att_o"], st["att_lse"])
+            if hd is not None:
+                hd.step(phase_mask=4, layer_begin=l, layer_end=l + 1)     # attention phase of the persistent kernel
+            else:
+                lib.ar_decode_attention(ws["qkv"], st["pk"][l], st["pv"][l], st["ck"][l], st["cv"][l], st["state"], B, H,
+                                        P, Nmax, ws["o"], st["att_o"], st["att_lse"])
             lib.gemm(ws["o"], lw["wproj"], M=B, N=D, K=D, out_f32=pa, outf_bstride=B * D, tile_n=32, splitk=max(s1, 2), cluster=cl)
             lib.residual_layernorm(x, B, D, pa, self._nsplit(kb, max(s1, 2)), B * D, lw["bproj"], lw["ln2_g"], lw["ln2_b"],
                                    out_bf16=ws["a"])

@@ -42,6 +42,7 @@ constexpr int AS_SMEM_TOTAL = AS_DATA_BYTES + AS_CTRL_BYTES + 1024;
 constexpr int AS_MAX_STAGES = 8;
 constexpr int AS_W_TILE_BYTES = 128 * 64 * 2;
 constexpr int AS_MAX_TILES = 512;                          // ticket counters (row tile x batch tile)
+constexpr int AS_SYNC_BAR_BYTES = 17 * 128;                // barrier epoch line + 16 arrival-counter lines
 
 enum { G_QKV = 0, G_PROJ = 1, G_FC = 2, G_PROJ2 = 3, G_HEAD = 4 };
 enum { OUT_PARTIAL = 0, OUT_BF16 = 1, OUT_F32 = 2 };
@@ -59,6 +60,8 @@ struct AsParams {
   int TB, nbt, nst, stage_bytes;          // batch tile (UMMA N), number of batch tiles, pipeline stages
   int ncph, ipr, team;                    // attention: CTAs per head, items per round, warps per item
   int prefetch;
+  int sync_mode;                          // grid barrier flavour (TTB_AR_STEP_SYNC): 0 = conservative, 1 = light
+  int ring_cp, ring_ns;                   // attention ring: positions per stage (8 / 16) and stages per warp (2..4)
   int layer_begin, layer_end, phase_mask; // debug / profiling: subset of the step (phase_mask bit i = phase i of a layer)
   AsGemmShape g[5];
   const CUtensorMap* maps;                // device: [4*L + 1] weight maps, then activation maps a, o, h, hn
@@ -74,12 +77,13 @@ struct AsParams {
   float* logits;
   const __nv_bfloat16* prefix_kv;         // [L][H][P][2][64]
   __nv_bfloat16* cand_kv;                 // [L][B][H][Nmax][2][64]
-  unsigned long long* bar;                // [0] arrivals (monotonic), [1] value of [0] when this launch started
+  unsigned long long* bar;                // [0] barrier epoch at launch; arrival slots at [16 * (1 + k)], k < 16
   unsigned int* tickets;                  // [AS_MAX_TILES]
 };
 
 // phase bits (phase_mask)
-enum { PH_EMBED = 1, PH_QKV = 2, PH_ATTN = 4, PH_PROJ = 8, PH_LN2 = 16, PH_FC = 32, PH_PROJ2 = 64, PH_LN1 = 128, PH_HEAD = 256 };
+enum { PH_EMBED = 1, PH_QKV = 2, PH_ATTN = 4, PH_PROJ = 8, PH_LN2 = 16, PH_FC = 32, PH_PROJ2 = 64, PH_LN1 = 128, PH_HEAD = 256,
+       PH_NOP = 512 /* probe: one empty grid barrier per layer */ };
 
 // ------------------------------------------------------------------ small device helpers
 TTB_DEVINL void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -134,7 +138,7 @@ struct AsCtrl {                       // lives in the control block of shared me
   uint64_t full_bar[AS_MAX_STAGES];
   uint64_t empty_bar[AS_MAX_STAGES];
   uint64_t acc_full, acc_empty;
-  uint64_t ring_bar[AS_WARPS][2];
+  uint64_t ring_bar[AS_WARPS][4];
   uint64_t prefix_bar;
   uint32_t tmem_slot;
   uint32_t ticket;
@@ -147,34 +151,52 @@ struct AsRole {                       // per-thread pipeline bookkeeping that su
   int stage;                          // GEMM smem ring position (producer and MMA thread keep identical copies)
   uint32_t phase;
   uint32_t acc_par;                   // accumulator full/empty parity (MMA thread and epilogue threads)
-  uint32_t ring_par[2];               // attention ring parities of this warp
+  uint32_t ring_par[4];               // attention ring parities of this warp
   uint32_t prefix_par;
   unsigned long long bar_target;      // next grid-barrier target
 };
 
 // ------------------------------------------------------------------ grid-wide barrier
+// Arrivals are spread over AS_BAR_SLOTS counters, each on its own 128-byte line: 148 same-address atomics serialise in one
+// L2 slice (~1 us of the 1.7 us the single-counter barrier cost); the first AS_BAR_SLOTS lanes of warp 0 poll one
+// counter each. Counters are monotonic: slot k ends barrier number E at E * (number of CTAs mapped to slot k).
+constexpr int AS_BAR_SLOTS = 16;
+constexpr int AS_BAR_STRIDE = 16;          // u64 elements between slots (128 bytes)
+
 TTB_DEVINL void grid_sync(const AsParams& p, AsRole& rl) {
   int* err = &p.state->reserved[0];
-  fence_proxy_async_all();            // generic-proxy writes of this phase before async-proxy (TMA / bulk) reads of the next
+  // generic-proxy writes of this phase must be ordered before async-proxy (TMA / bulk copy) reads of later phases
+  fence_proxy_async_all();
   __syncthreads();
-  rl.bar_target += gridDim.x;
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(p.bar, 1ULL);
+  rl.bar_target += 1;                     // barrier epoch
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    if (lane == 0) {
+      unsigned long long* slot = p.bar + AS_BAR_STRIDE * (1 + (blockIdx.x % AS_BAR_SLOTS));
+      if (p.sync_mode == 0) { __threadfence(); atomicAdd(slot, 1ULL); }
+      else asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(slot) : "memory");
+    }
     if (*reinterpret_cast<volatile int*>(err) == 0) {
-      const unsigned long long t0 = global_timer_ns();
+      // CTAs mapped to slot `lane`: blockIdx % SLOTS == lane
+      const unsigned long long cnt = (lane < AS_BAR_SLOTS) ? (gridDim.x + AS_BAR_SLOTS - 1 - lane) / AS_BAR_SLOTS : 0;
+      const unsigned long long want = rl.bar_target * cnt;
+      const unsigned long long* mine = p.bar + AS_BAR_STRIDE * (1 + (lane % AS_BAR_SLOTS));
+      unsigned long long t0 = 0;
       unsigned n = 0;
-      while (ld_acquire_u64(p.bar) < rl.bar_target) {
+      while (true) {
+        const bool ok = (lane >= AS_BAR_SLOTS) || (ld_acquire_u64(mine) >= want);
+        if (__all_sync(0xffffffffu, ok)) break;
         if ((++n & 0xff) == 0) {
-          if (*reinterpret_cast<volatile int*>(err) != 0) break;
-          if (global_timer_ns() - t0 > 2000000000ull) { *reinterpret_cast<volatile int*>(err) = 1; break; }
+          if (t0 == 0) t0 = global_timer_ns();
+          const bool stop = (*reinterpret_cast<volatile int*>(err) != 0) || (global_timer_ns() - t0 > 2000000000ull);
+          if (__any_sync(0xffffffffu, stop)) { if (lane == 0) *reinterpret_cast<volatile int*>(err) = 1; break; }
         }
       }
     }
-    __threadfence();
+    if (p.sync_mode == 0) __threadfence();
   }
   __syncthreads();
-  fence_proxy_async_all();
+  if (p.sync_mode == 0) fence_proxy_async_all();
 }
 
 // block-wide sum over 512 threads; `buf` is one of ctrl.red[i] (callers alternate buffers so one sync per reduction suffices)
@@ -254,16 +276,21 @@ TTB_DEVINL void gemm_phase(const AsParams& p, const AsGemmShape& g, const CUtens
         rl.acc_par ^= 1;
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ===== epilogue: warp w reads TMEM lanes [32 (w % 4), +32) = weight rows; columns = candidates =====
+  } else if (warp >= 4) {
+    // ===== warps 4..7: epilogue (warp w reads TMEM lanes [32 (w % 4), +32) = weight rows; columns = candidates) =====
+    // ===== warps 8..15: idle during the main loop; they join the split-K fix-up of ticketed GEMMs (384 threads) =====
+    const bool epi = warp < 8;
+    const bool ticketed = (OUT != OUT_PARTIAL) && g.nsplit > 1;
+    if (!epi && !ticketed) return;
     const int q = warp & 3;
-    const int et = threadIdx.x - 128;                  // 0..127
+    const int et = threadIdx.x - 128;                  // 0..383 (epilogue threads first)
     for (int item = blockIdx.x; item < g.items; item += gridDim.x) {
       const int ks = item % g.nsplit;
       const int t = item / g.nsplit;
       const int bt = t % p.nbt, rt = t / p.nbt;
       const int n = rt * 128 + q * 32 + lane;
       const int b_lo = bt * TB;
+      if (epi) {
       mbar_wait_to(&ctrl->acc_full, rl.acc_par, err);
       rl.acc_par ^= 1;
       tc_fence_after();
@@ -294,15 +321,16 @@ TTB_DEVINL void gemm_phase(const AsParams& p, const AsGemmShape& g, const CUtens
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctrl->acc_empty);     // count 4: one arrive per epilogue warp
-      if (OUT != OUT_PARTIAL && g.nsplit > 1) {
+      }
+      if (ticketed) {
         // ticket: the last split to arrive reduces the tile in split order (deterministic), adds bias, activates, writes
-        __threadfence();
-        named_bar_sync(1, 128);
+        if (epi) __threadfence();
+        named_bar_sync(1, 384);
         const int tile = rt * p.nbt + bt;
         if (et == 0) ctrl->ticket = atomicAdd(&p.tickets[tile], 1u);
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 384);
         const bool last = (ctrl->ticket == (uint32_t)(g.nsplit - 1));
-        named_bar_sync(1, 128);                          // ticket slot may be rewritten by the next item
+        named_bar_sync(1, 384);                          // ticket slot may be rewritten by the next item
         if (last) {
           __threadfence();
           const int nb = min(TB, p.B - b_lo);
@@ -316,30 +344,56 @@ TTB_DEVINL void gemm_phase(const AsParams& p, const AsGemmShape& g, const CUtens
               if (n4 + 2 < g.Nrows) bb.z = __ldg(bias + n4 + 2);
               if (n4 + 3 < g.Nrows) bb.w = __ldg(bias + n4 + 3);
             }
-            for (int bi = (et >> 5); bi < nb; bi += 4) {
-              const int b = b_lo + bi;
-              float4 s = bb;
-              for (int sp = 0; sp < g.nsplit; ++sp) {
-                const float4 v = __ldcg(reinterpret_cast<const float4*>(p.part + ((long long)sp * p.B + b) * g.ldp + n4));
-                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-              }
-              if (ACT == TTB_ACT_GELU_NEW) { s.x = gelu_new(s.x); s.y = gelu_new(s.y); s.z = gelu_new(s.z); s.w = gelu_new(s.w); }
-              if (OUT == OUT_BF16) {
-                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out) + (long long)b * ldo + n4;
-                if (n4 + 3 < g.Nrows && (ldo & 3) == 0) {
-                  *reinterpret_cast<uint2*>(op) = make_uint2(pack_bf16(s.x, s.y), pack_bf16(s.z, s.w));
-                } else {
-                  op[0] = __float2bfloat16(s.x);
-                  if (n4 + 1 < g.Nrows) op[1] = __float2bfloat16(s.y);
-                  if (n4 + 2 < g.Nrows) op[2] = __float2bfloat16(s.z);
-                  if (n4 + 3 < g.Nrows) op[3] = __float2bfloat16(s.w);
+            // 4 rows x all splits in flight per thread before the first add (a dependent chain of L2 round trips
+            // made this fix-up cost 10-25 us per GEMM in the first version)
+            constexpr int FX_ROWS = 2, FX_SPLITS = 4, FX_LANES = 12;      // 384 threads = 32 column groups x 12 row lanes
+            for (int bi0 = (et >> 5); bi0 < nb; bi0 += FX_LANES * FX_ROWS) {
+              float4 acc[FX_ROWS];
+#pragma unroll
+              for (int r = 0; r < FX_ROWS; ++r) acc[r] = bb;
+              for (int sp0 = 0; sp0 < g.nsplit; sp0 += FX_SPLITS) {
+                float4 v[FX_ROWS][FX_SPLITS];
+#pragma unroll
+                for (int r = 0; r < FX_ROWS; ++r) {
+                  const int bi = bi0 + FX_LANES * r;
+#pragma unroll
+                  for (int u = 0; u < FX_SPLITS; ++u) {
+                    v[r][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bi < nb && sp0 + u < g.nsplit)
+                      v[r][u] = __ldcg(reinterpret_cast<const float4*>(p.part + ((long long)(sp0 + u) * p.B + b_lo + bi) * g.ldp + n4));
+                  }
                 }
-              } else {
-                float* op = reinterpret_cast<float*>(out) + (long long)b * ldo + n4;
-                op[0] = s.x;
-                if (n4 + 1 < g.Nrows) op[1] = s.y;
-                if (n4 + 2 < g.Nrows) op[2] = s.z;
-                if (n4 + 3 < g.Nrows) op[3] = s.w;
+#pragma unroll
+                for (int r = 0; r < FX_ROWS; ++r)
+#pragma unroll
+                  for (int u = 0; u < FX_SPLITS; ++u) {       // fixed split order: deterministic
+                    acc[r].x += v[r][u].x; acc[r].y += v[r][u].y; acc[r].z += v[r][u].z; acc[r].w += v[r][u].w;
+                  }
+              }
+#pragma unroll
+              for (int r = 0; r < FX_ROWS; ++r) {
+                const int bi = bi0 + FX_LANES * r;
+                if (bi >= nb) continue;
+                const int b = b_lo + bi;
+                float4 s = acc[r];
+                if (ACT == TTB_ACT_GELU_NEW) { s.x = gelu_new(s.x); s.y = gelu_new(s.y); s.z = gelu_new(s.z); s.w = gelu_new(s.w); }
+                if (OUT == OUT_BF16) {
+                  __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out) + (long long)b * ldo + n4;
+                  if (n4 + 3 < g.Nrows && (ldo & 3) == 0) {
+                    *reinterpret_cast<uint2*>(op) = make_uint2(pack_bf16(s.x, s.y), pack_bf16(s.z, s.w));
+                  } else {
+                    op[0] = __float2bfloat16(s.x);
+                    if (n4 + 1 < g.Nrows) op[1] = __float2bfloat16(s.y);
+                    if (n4 + 2 < g.Nrows) op[2] = __float2bfloat16(s.z);
+                    if (n4 + 3 < g.Nrows) op[3] = __float2bfloat16(s.w);
+                  }
+                } else {
+                  float* op = reinterpret_cast<float*>(out) + (long long)b * ldo + n4;
+                  op[0] = s.x;
+                  if (n4 + 1 < g.Nrows) op[1] = s.y;
+                  if (n4 + 2 < g.Nrows) op[2] = s.z;
+                  if (n4 + 3 < g.Nrows) op[3] = s.w;
+                }
               }
             }
           }
@@ -362,22 +416,24 @@ TTB_DEVINL float as_dot8(const float* q, const uint4& kk) {
   return d;
 }
 
-// 16 positions [pos][K|V] at `buf` (shared memory), npos valid. lane = (psub = lane >> 3, dch = lane & 7): position
+// CP positions [pos][K|V] at `buf` (shared memory), npos valid. lane = (psub = lane >> 3, dch = lane & 7): position
 // psub + 4u, dims [8 dch, 8 dch + 8). One shared running-max update per call.
+template <int CP>
 TTB_DEVINL void as_chunk(AttState& st, const float* q, const uint8_t* buf, int npos, int psub, int dch) {
-  uint4 kk[4], vv[4];
+  constexpr int U = CP / 4;
+  uint4 kk[U], vv[U];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
+  for (int u = 0; u < U; ++u) {
     const uint8_t* pp = buf + (psub + 4 * u) * AS_POS_BYTES + dch * 16;
     kk[u] = *reinterpret_cast<const uint4*>(pp);
     vv[u] = *reinterpret_cast<const uint4*>(pp + 128);
     // rows past npos hold stale bytes (possibly NaN patterns): their weight is exactly 0, so V must be finite
     if (psub + 4 * u >= npos) vv[u] = make_uint4(0, 0, 0, 0);
   }
-  float s[4];
+  float s[U];
   float bm = -INFINITY;
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
+  for (int u = 0; u < U; ++u) {
     s[u] = as_dot8(q, kk[u]);
     s[u] = (psub + 4 * u < npos) ? s[u] : -INFINITY;
     bm = fmaxf(bm, s[u]);
@@ -390,7 +446,7 @@ TTB_DEVINL void as_chunk(AttState& st, const float* q, const uint8_t* buf, int n
 #pragma unroll
   for (int d = 0; d < 8; ++d) st.acc[d] *= corr;
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
+  for (int u = 0; u < U; ++u) {
     const float pw = exp2f(s[u] - m_use);
     st.l += pw;
     const float2 f0 = unpack_bf16(vv[u].x), f1 = unpack_bf16(vv[u].y), f2 = unpack_bf16(vv[u].z), f3 = unpack_bf16(vv[u].w);
@@ -409,15 +465,18 @@ TTB_DEVINL void as_merge(AttState& st, float m_o, float l_o, const float* a_o) {
   st.m = m_new;
 }
 
+template <int CP>
 TTB_DEVINL void attn_phase(const AsParams& p, int layer, uint8_t* data, AsCtrl* ctrl, AsRole& rl) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int psub = lane >> 3, dch = lane & 7;
   int* err = &p.state->reserved[0];
   const int B = p.B, H = p.H, P = p.P, Nmax = p.Nmax, D = p.H * 64;
+  const int NS = p.ring_ns;
+  constexpr int CHUNK_BYTES = CP * AS_POS_BYTES;
   const int slot = p.state->step - 1;                  // the token fed at this step lands in cache slot `slot`
   const int nold = slot;                               // positions already in the candidate cache
-  uint8_t* prefix_s = data + AS_RING_BYTES;
-  uint8_t* ring = data + warp * 2 * AS_CHUNK_BYTES;
+  uint8_t* ring = data + warp * NS * CHUNK_BYTES;
+  uint8_t* prefix_s = data + AS_WARPS * NS * CHUNK_BYTES;      // behind the rings (host checks that P fits)
   const __nv_bfloat16* pkv_l = p.prefix_kv + (long long)layer * H * P * 128;
   __nv_bfloat16* ckv_l = p.cand_kv + (long long)layer * B * H * Nmax * 128;
   const int units = H * p.ncph;
@@ -451,21 +510,17 @@ TTB_DEVINL void attn_phase(const AsParams& p, int layer, uint8_t* data, AsCtrl* 
         const uint4 k_new = __ldcg(reinterpret_cast<const uint4*>(qrow + D) + dch);
         const uint4 v_new = __ldcg(reinterpret_cast<const uint4*>(qrow + 2 * D) + dch);
         // ---- the candidate's own cache, through this warp's ring (chunks sub, sub + team, ...)
-        const int nch = (nold + AS_CHUNK_POS - 1) / AS_CHUNK_POS;
-        int c_issue = sub, c_use = sub;
+        const int nch = (nold + CP - 1) / CP;
         if (lane == 0) {
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            if (c_issue < nch) {
-              const int np = min(AS_CHUNK_POS, nold - c_issue * AS_CHUNK_POS);
+          for (int s = 0; s < NS; ++s) {
+            const int c = sub + s * p.team;
+            if (c < nch) {
+              const int np = min(CP, nold - c * CP);
               mbar_arrive_expect_tx(&ctrl->ring_bar[warp][s], (uint32_t)(np * AS_POS_BYTES));
-              bulk_g2s(ring + s * AS_CHUNK_BYTES, cb + (long long)c_issue * AS_CHUNK_POS * 128, (uint32_t)(np * AS_POS_BYTES),
-                       &ctrl->ring_bar[warp][s]);
+              bulk_g2s(ring + s * CHUNK_BYTES, cb + (long long)c * CP * 128, (uint32_t)(np * AS_POS_BYTES), &ctrl->ring_bar[warp][s]);
             }
-            c_issue += p.team;
           }
         }
-        c_issue = sub + 2 * p.team;
         if (sub == 0) {
           // append the new K / V rows (lanes 0-7: K chunks, 8-15: V chunks) and account for them from registers
           if (lane < 16) reinterpret_cast<uint4*>(cb + (long long)slot * 128 + (lane < 8 ? 0 : 64))[dch] = (lane < 8) ? k_new : v_new;
@@ -478,26 +533,25 @@ TTB_DEVINL void attn_phase(const AsParams& p, int layer, uint8_t* data, AsCtrl* 
           }
         }
         int s = 0;
-        for (; c_use < nch; c_use += p.team) {
+        for (int c_use = sub; c_use < nch; c_use += p.team) {
           mbar_wait_to(&ctrl->ring_bar[warp][s], rl.ring_par[s], err);
           rl.ring_par[s] ^= 1;
-          const int np = min(AS_CHUNK_POS, nold - c_use * AS_CHUNK_POS);
-          as_chunk(st, q, ring + s * AS_CHUNK_BYTES, np, psub, dch);
+          const int np = min(CP, nold - c_use * CP);
+          as_chunk<CP>(st, q, ring + s * CHUNK_BYTES, np, psub, dch);
           __syncwarp();
-          if (lane == 0 && c_issue < nch) {
-            const int np2 = min(AS_CHUNK_POS, nold - c_issue * AS_CHUNK_POS);
+          const int c_next = c_use + NS * p.team;
+          if (lane == 0 && c_next < nch) {
+            const int np2 = min(CP, nold - c_next * CP);
             mbar_arrive_expect_tx(&ctrl->ring_bar[warp][s], (uint32_t)(np2 * AS_POS_BYTES));
-            bulk_g2s(ring + s * AS_CHUNK_BYTES, cb + (long long)c_issue * AS_CHUNK_POS * 128, (uint32_t)(np2 * AS_POS_BYTES),
-                     &ctrl->ring_bar[warp][s]);
+            bulk_g2s(ring + s * CHUNK_BYTES, cb + (long long)c_next * CP * 128, (uint32_t)(np2 * AS_POS_BYTES), &ctrl->ring_bar[warp][s]);
           }
-          c_issue += p.team;
-          s ^= 1;
+          if (++s == NS) s = 0;
         }
         // ---- the shared prompt prefix of this head, from shared memory
         mbar_wait_to(&ctrl->prefix_bar, rl.prefix_par, err);
-        const int npc = (P + AS_CHUNK_POS - 1) / AS_CHUNK_POS;
+        const int npc = (P + 15) / 16;
         for (int c = sub; c < npc; c += p.team)
-          as_chunk(st, q, prefix_s + c * AS_CHUNK_BYTES, min(AS_CHUNK_POS, P - c * AS_CHUNK_POS), psub, dch);
+          as_chunk<16>(st, q, prefix_s + c * 16 * AS_POS_BYTES, min(16, P - c * 16), psub, dch);
         // ---- merge the 4 position sub-streams of the warp
 #pragma unroll
         for (int off = 8; off <= 16; off <<= 1) {
@@ -564,8 +618,16 @@ TTB_DEVINL void ln_phase(const AsParams& p, int mode, const float* part, int nsp
         float a = 0.f;
         if (c < D) {
           float acc = rbias ? __ldg(rbias + c) : 0.f;
-          for (int sp = 0; sp < nsplit; ++sp) acc += __ldcg(part + ((long long)sp * p.B + row) * ldp + c);
-          a = __ldcg(p.x + (long long)row * D + c) + acc;
+          const float xv = __ldcg(p.x + (long long)row * D + c);
+          for (int sp0 = 0; sp0 < nsplit; sp0 += 8) {          // all loads first, then the adds in split order
+            float pv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              pv[u] = (sp0 + u < nsplit) ? __ldcg(part + ((long long)(sp0 + u) * p.B + row) * ldp + c) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += pv[u];
+          }
+          a = xv + acc;
         }
         v[i] = a;
       }
@@ -616,7 +678,8 @@ __global__ void __launch_bounds__(AS_THREADS, 1) ar_step_kernel(const __grid_con
     for (int s = 0; s < AS_MAX_STAGES; ++s) { mbar_init(&ctrl->full_bar[s], 1); mbar_init(&ctrl->empty_bar[s], 1); }
     mbar_init(&ctrl->acc_full, 1);
     mbar_init(&ctrl->acc_empty, 4);
-    for (int w = 0; w < AS_WARPS; ++w) { mbar_init(&ctrl->ring_bar[w][0], 1); mbar_init(&ctrl->ring_bar[w][1], 1); }
+    for (int w = 0; w < AS_WARPS; ++w)
+      for (int k = 0; k < 4; ++k) mbar_init(&ctrl->ring_bar[w][k], 1);
     mbar_init(&ctrl->prefix_bar, 1);
     fence_barrier_init();
   }
@@ -627,8 +690,9 @@ __global__ void __launch_bounds__(AS_THREADS, 1) ar_step_kernel(const __grid_con
   const uint32_t tmem_base = ctrl->tmem_slot;
 
   AsRole rl;
-  rl.stage = 0; rl.phase = 0; rl.acc_par = 0; rl.ring_par[0] = 0; rl.ring_par[1] = 0; rl.prefix_par = 0;
-  rl.bar_target = ld_acquire_u64(p.bar + 1);
+  rl.stage = 0; rl.phase = 0; rl.acc_par = 0; rl.prefix_par = 0;
+  rl.ring_par[0] = rl.ring_par[1] = rl.ring_par[2] = rl.ring_par[3] = 0;
+  rl.bar_target = ld_acquire_u64(p.bar);          // barrier epoch at launch (bar[0]; the arrival slots follow)
 
   const CUtensorMap* map_a = p.maps + 4 * p.L + 1;
   const CUtensorMap* map_o = map_a + 1;
@@ -636,6 +700,12 @@ __global__ void __launch_bounds__(AS_THREADS, 1) ar_step_kernel(const __grid_con
   const CUtensorMap* map_hn = map_a + 3;
   const bool pf = p.prefetch && warp == 2 && lane == 0;
   const int L0 = p.layer_begin, L1 = p.layer_end;
+  // the barrier behind the last phase of the launch orders nothing (the kernel boundary does): skip it
+  int last_bit = 0;
+  for (int b = 0; b < 10; ++b) if (p.phase_mask & (1 << b)) last_bit = b;
+  const bool head_follows = (p.phase_mask & PH_HEAD) != 0;
+#define AS_SYNC_UNLESS_LAST(bit, layer) \
+  do { if (head_follows || (layer) + 1 < L1 || (bit) != last_bit) grid_sync(p, rl); } while (0)
 
   if (p.phase_mask & PH_EMBED) {
     if (pf && L0 < L1) prefetch_gemm_item(p, p.maps + 4 * L0 + G_QKV, p.g[G_QKV]);
@@ -649,20 +719,22 @@ __global__ void __launch_bounds__(AS_THREADS, 1) ar_step_kernel(const __grid_con
     if (p.phase_mask & PH_QKV) {
       if (pf) { prefetch_gemm_item(p, mw + G_PROJ, p.g[G_PROJ]); prefetch_gemm_item(p, mw + G_FC, p.g[G_FC]); }
       gemm_phase<OUT_BF16, TTB_ACT_NONE>(p, p.g[G_QKV], mw + G_QKV, map_a, lw.bqkv, p.qkv, 3 * p.D, data, ctrl, rl, tmem_base);
-      grid_sync(p, rl);
+      AS_SYNC_UNLESS_LAST(1, l);
     }
     if (p.phase_mask & PH_ATTN) {
-      attn_phase(p, l, data, ctrl, rl);
-      grid_sync(p, rl);
+      if (p.ring_cp == 8) attn_phase<8>(p, l, data, ctrl, rl);
+      else attn_phase<16>(p, l, data, ctrl, rl);
+      AS_SYNC_UNLESS_LAST(2, l);
     }
+    if (p.phase_mask & PH_NOP) grid_sync(p, rl);
     if (p.phase_mask & PH_PROJ) {
       if (pf) prefetch_gemm_item(p, mw + G_PROJ2, p.g[G_PROJ2]);
       gemm_phase<OUT_PARTIAL, TTB_ACT_NONE>(p, p.g[G_PROJ], mw + G_PROJ, map_o, nullptr, nullptr, 0, data, ctrl, rl, tmem_base);
-      grid_sync(p, rl);
+      AS_SYNC_UNLESS_LAST(3, l);
     }
     if (p.phase_mask & PH_LN2) {
       ln_phase(p, 1, p.part, p.g[G_PROJ].nsplit, p.g[G_PROJ].ldp, lw.bproj, lw.ln2_g, lw.ln2_b, nullptr, nullptr, p.a, ctrl);
-      grid_sync(p, rl);
+      AS_SYNC_UNLESS_LAST(4, l);
     }
     if (p.phase_mask & PH_FC) {
       if (pf) {
@@ -670,11 +742,11 @@ __global__ void __launch_bounds__(AS_THREADS, 1) ar_step_kernel(const __grid_con
         else prefetch_gemm_item(p, p.maps + 4 * p.L, p.g[G_HEAD]);
       }
       gemm_phase<OUT_BF16, TTB_ACT_GELU_NEW>(p, p.g[G_FC], mw + G_FC, map_a, lw.bfc, p.h, 4 * p.D, data, ctrl, rl, tmem_base);
-      grid_sync(p, rl);
+      AS_SYNC_UNLESS_LAST(5, l);
     }
     if (p.phase_mask & PH_PROJ2) {
       gemm_phase<OUT_PARTIAL, TTB_ACT_NONE>(p, p.g[G_PROJ2], mw + G_PROJ2, map_h, nullptr, nullptr, 0, data, ctrl, rl, tmem_base);
-      grid_sync(p, rl);
+      AS_SYNC_UNLESS_LAST(6, l);
     }
     if (p.phase_mask & PH_LN1) {
       if (l + 1 < p.L) {
@@ -683,7 +755,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1) ar_step_kernel(const __grid_con
       } else {
         ln_phase(p, 1, p.part, p.g[G_PROJ2].nsplit, p.g[G_PROJ2].ldp, lw.bproj2, p.lnf_g, p.lnf_b, p.fn_g, p.fn_b, p.hn, ctrl);
       }
-      grid_sync(p, rl);
+      AS_SYNC_UNLESS_LAST(7, l);
     }
   }
   if (p.phase_mask & PH_HEAD) {
@@ -697,8 +769,8 @@ __global__ void __launch_bounds__(AS_THREADS, 1) ar_step_kernel(const __grid_con
     tmem_dealloc<256>(tmem_base);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    // every CTA has read bar[1] before its first arrival, and all arrivals of this launch precede this point
-    *reinterpret_cast<volatile unsigned long long*>(p.bar + 1) = rl.bar_target;
+    // every CTA has read the epoch before its first arrival, and all arrivals of this launch precede this point
+    *reinterpret_cast<volatile unsigned long long*>(p.bar) = rl.bar_target;
   }
 }
 
@@ -764,7 +836,7 @@ static int make_plan(const TtbArStepArgs& a, AsPlan& pl) {
   p.stage_bytes = AS_W_TILE_BYTES + p.TB * 128;
   p.nst = AS_DATA_BYTES / p.stage_bytes;
   if (p.nst > AS_MAX_STAGES) p.nst = AS_MAX_STAGES;
-  const int cap_f = env_int("TTB_AR_STEP_SPLIT_FINAL", 8);
+  const int cap_f = env_int("TTB_AR_STEP_SPLIT_FINAL", 8);      // try 1 at B > 128: direct epilogue, no fix-up
   const int cap_p = env_int("TTB_AR_STEP_SPLIT_PART", p.nbt > 1 ? 4 : 8);
   plan_gemm(p.g[G_QKV], 3 * a.D, a.D, p.nbt, grid, cap_f);
   plan_gemm(p.g[G_PROJ], a.D, a.D, p.nbt, grid, cap_p);
@@ -791,9 +863,22 @@ static int make_plan(const TtbArStepArgs& a, AsPlan& pl) {
   if (tcap > 0 && tcap < team) team = tcap;
   p.team = team;
   p.prefetch = env_int("TTB_AR_STEP_PREFETCH", 1);
+  p.sync_mode = env_int("TTB_AR_STEP_SYNC", 1);
+  p.ring_cp = env_int("TTB_AR_STEP_RING_CP", 16) == 8 ? 8 : 16;
+  p.ring_ns = env_int("TTB_AR_STEP_RING_NS", 2);
+  if (p.ring_ns < 2) p.ring_ns = 2;
+  if (p.ring_ns > 4) p.ring_ns = 4;
+  // the rings of all warps + the prompt prefix of one head share the data region
+  while (p.ring_ns > 2 && AS_WARPS * p.ring_ns * p.ring_cp * AS_POS_BYTES + ((a.P + 15) & ~15) * AS_POS_BYTES > AS_DATA_BYTES) --p.ring_ns;
+  if (AS_WARPS * p.ring_ns * p.ring_cp * AS_POS_BYTES + ((a.P + 15) & ~15) * AS_POS_BYTES > AS_DATA_BYTES) {
+    set_error("ttb_ar_step: ring %d x %d positions + prompt %d do not fit shared memory", p.ring_ns, p.ring_cp, a.P);
+    return -1;
+  }
   p.layer_begin = 0; p.layer_end = a.L; p.phase_mask = 0x1ff;
   if (a.debug_layer_end > 0) { p.layer_begin = a.debug_layer_begin; p.layer_end = a.debug_layer_end; }
   if (a.debug_phase_mask) p.phase_mask = a.debug_phase_mask;
+  const int pcap = env_int("TTB_AR_STEP_PROJ2_SPLIT", 0);      // experiments: split count of mlp.c_proj alone
+  if (pcap > 0) plan_gemm(p.g[G_PROJ2], a.D, 4 * a.D, p.nbt, grid, pcap);
   return 0;
 }
 
@@ -810,7 +895,7 @@ extern "C" int ttb_ar_step_workspace(const TtbArStepArgs* a, long long* part_flo
   if (make_plan(*a, pl)) return -1;
   if (part_floats) *part_floats = pl.part_floats;
   if (table_bytes_out) *table_bytes_out = table_bytes(a->L);
-  if (sync_bytes) *sync_bytes = 64 + AS_MAX_TILES * 4;
+  if (sync_bytes) *sync_bytes = AS_SYNC_BAR_BYTES + AS_MAX_TILES * 4;
   return 0;
 }
 
@@ -845,7 +930,7 @@ extern "C" int ttb_ar_step_setup(const TtbArStepArgs* ap, void* stream) {
   if (get_tensor_map_bf16(&am[2], a.h, 4 * D, Bq, 1, 4 * D, Bq * 4 * D, 64, TB)) return -1;
   if (get_tensor_map_bf16(&am[3], a.hn, D, Bq, 1, D, Bq * D, 64, TB)) return -1;
   cudaError_t e = cudaMemcpyAsync(a.tables, host.data(), host.size(), cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(a.sync, 0, 64 + AS_MAX_TILES * 4, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(a.sync, 0, AS_SYNC_BAR_BYTES + AS_MAX_TILES * 4, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return check_cuda(e, "ttb_ar_step_setup");
   static bool attr_set = false;
@@ -876,7 +961,7 @@ extern "C" int ttb_ar_decode_step(const TtbArStepArgs* ap, void* stream) {
   p.prefix_kv = reinterpret_cast<const __nv_bfloat16*>(a.prefix_kv);
   p.cand_kv = reinterpret_cast<__nv_bfloat16*>(a.cand_kv);
   p.bar = reinterpret_cast<unsigned long long*>(a.sync);
-  p.tickets = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(a.sync) + 64);
+  p.tickets = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(a.sync) + AS_SYNC_BAR_BYTES);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pl.grid);
   cfg.blockDim = dim3(AS_THREADS);
