@@ -138,10 +138,12 @@ def test_step_gemm_and_norm_phases(B, D, H, V, P):
 
 
 @pytest.mark.parametrize("B,H,P", [(256, 16, 174), (32, 16, 174), (64, 16, 352), (7, 2, 13)])
-@pytest.mark.parametrize("nc", [1, 7, 8, 9, 16, 17, 215, 429])
-def test_step_attention_phase(B, H, P, nc):
+@pytest.mark.parametrize("nc", [1, 7, 8, 9, 16, 17, 33, 215, 429])
+@pytest.mark.parametrize("impl", ["mma", "simt"])
+def test_step_attention_phase(B, H, P, nc, impl, monkeypatch):
     """Decode attention over [shared prompt prefix | own KV | new token] + the KV append, at `nc` candidate entries
     (incl. the new one): all chunk-boundary cases of the 16-position ring and the production context lengths."""
+    monkeypatch.setenv("TTB_AR_STEP_ATTN_MMA", "1" if impl == "mma" else "0")   # read at every launch (make_plan)
     D, L, V, Nmax = H * 64, 2, 300, 430
     step = nc                                         # slot = step - 1 = nc - 1 old entries, + the new one
     hd, t = _mk(B, D, H, L, V, P, Nmax, step, seed=nc + B)
@@ -165,8 +167,10 @@ def test_step_attention_phase(B, H, P, nc):
     Vv = torch.cat([pv, ck[:, :, :slot + 1, 1].float()], dim=2)
     want = (torch.softmax(q @ K.transpose(-1, -2), -1) @ Vv).reshape(B, D)
     r = _rel(t["o"], want)
-    report("ar_step attention B=%d P=%d nc=%d" % (B, P, nc), r)
-    assert r < 6e-3                                   # fp32 math, bf16 store
+    report("ar_step attention %s B=%d P=%d nc=%d" % (impl, B, P, nc), r)
+    # simt: fp32 weights, bf16 store (2^-9). mma: the softmax weights are rounded to bf16 for the P V product, as in every
+    # flash-attention kernel (and in round 1's prompt part): 2^-9 relative on each weight, averaged over the row
+    assert r < (8e-3 if impl == "mma" else 6e-3)
 
 
 @pytest.mark.parametrize("B", [256, 32, 3])

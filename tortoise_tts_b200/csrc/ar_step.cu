@@ -62,6 +62,7 @@ struct AsParams {
   int prefetch;
   int sync_mode;                          // grid barrier flavour (TTB_AR_STEP_SYNC): 0 = conservative, 1 = light
   int ring_cp, ring_ns;                   // attention ring: positions per stage (8 / 16) and stages per warp (2..4)
+  int attn_impl;                          // 1 = tensor-core (mma.sync) scores / PV from TMA-swizzled tiles, 0 = SIMT
   int layer_begin, layer_end, phase_mask; // debug / profiling: subset of the step (phase_mask bit i = phase i of a layer)
   AsGemmShape g[5];
   const CUtensorMap* maps;                // device: [4*L + 1] weight maps, then activation maps a, o, h, hn
@@ -109,10 +110,11 @@ TTB_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded wait: a protocol error must end as an error flag, not as a hung GPU. ~2 s budget.
 TTB_DEVINL void mbar_wait_to(uint64_t* bar, uint32_t parity, int* err) {
   if (mbar_try_wait(bar, parity)) return;
-  const unsigned long long t0 = global_timer_ns();
+  unsigned long long t0 = 0;             // %globaltimer is slow to read: only once the wait is already long
   unsigned n = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++n & 0x3ff) == 0) {
+      if (t0 == 0) t0 = global_timer_ns();
       if (*reinterpret_cast<volatile int*>(err) != 0) return;
       if (global_timer_ns() - t0 > 2000000000ull) { *reinterpret_cast<volatile int*>(err) = 2; return; }
     }
@@ -476,7 +478,7 @@ TTB_DEVINL void attn_phase(const AsParams& p, int layer, uint8_t* data, AsCtrl* 
   const int slot = p.state->step - 1;                  // the token fed at this step lands in cache slot `slot`
   const int nold = slot;                               // positions already in the candidate cache
   uint8_t* ring = data + warp * NS * CHUNK_BYTES;
-  uint8_t* prefix_s = data + AS_WARPS * NS * CHUNK_BYTES;      // behind the rings (host checks that P fits)
+  uint8_t* prefix_s = data + p.ipr * p.team * NS * CHUNK_BYTES;   // behind the rings of the active warps (host checks the fit)
   const __nv_bfloat16* pkv_l = p.prefix_kv + (long long)layer * H * P * 128;
   __nv_bfloat16* ckv_l = p.cand_kv + (long long)layer * B * H * Nmax * 128;
   const int units = H * p.ncph;
@@ -585,6 +587,226 @@ TTB_DEVINL void attn_phase(const AsParams& p, int layer, uint8_t* data, AsCtrl* 
         reinterpret_cast<uint4*>(p.o + (long long)b * D + h * 64)[dch] = o4;
       }
       if (p.team > 1) __syncthreads();                 // merge scratch is rewritten by the next round
+    }
+    rl.prefix_par ^= 1;
+  }
+}
+
+// ------------------------------------------------------------------ attention phase, tensor-core form
+// The SIMT form above spends ~14 issue slots per cached position (bf16 unpacking, 8-lane dot products, shuffles): at 256
+// candidates the phase is issue-bound (54 us against 41 us of KV traffic), the shared prompt part alone is 45 % of it.
+// Here both products of a 16-position chunk run on the tensor cores (mma.sync m16n8k16, bf16 in / fp32 out):
+//   S[16 pos] = K[16 x 64] q      : A = K chunk (row = position), B = q in column 0 of the 16 x 8 operand
+//   O[64]    += V^T[64 x 16] p    : A = V chunk read transposed (ldmatrix.trans), B = p (bf16) in column 0
+// 7/8 of every MMA is padding - the tensor pipe is idle anyway, what matters is ~3 issue slots per position.
+// K and V rows are separate 2 KB tiles in shared memory, written by TMA with the 128-byte swizzle, so that the eight
+// 16-byte rows of an ldmatrix fall into distinct banks (the 256-byte position pitch of the raw cache would alias them).
+TTB_DEVINL void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+TTB_DEVINL void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+TTB_DEVINL void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+TTB_DEVINL void mma_bf16_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+struct MmaState {
+  float m;             // running max (log2 domain), warp-uniform
+  float l;             // this lane's share of the running sum
+  float acc[4][4];     // O^T accumulators: dim block db, fragment regs; column 0 lives in lanes with lane % 4 == 0:
+                       //   acc[db][0] = O[16 db + lane/4], acc[db][2] = O[16 db + lane/4 + 8]
+};
+
+// one chunk: K tile / V tile (16 rows x 128 B, SWIZZLE_128B) at shared addresses kt / vt, npos valid rows
+TTB_DEVINL void mma_chunk(MmaState& st, const uint32_t* qb, uint32_t kt, uint32_t vt, int npos, int lane) {
+  const int mi = lane >> 3, r = lane & 7;
+  const int pos = r + 8 * (mi & 1);                       // row this lane addresses for K (matrices 0/1: rows 0-7 / 8-15)
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a0, a1, a2, a3;
+    const int ch = ks * 2 + (mi >> 1);                    // 16-byte chunk (8 dims) inside the 128-byte row
+    ldsm_x4(kt + pos * 128 + ((ch ^ (pos & 7)) << 4), a0, a1, a2, a3);
+    mma_bf16_16816(s, a0, a1, a2, a3, qb[2 * ks], qb[2 * ks + 1]);
+  }
+  const bool act = (lane & 3) == 0;
+  const int j = lane >> 2;
+  const float sc = 0.125f * 1.4426950408889634f;          // 1/sqrt(64) and log2(e)
+  float s_lo = (act && j < npos) ? s[0] * sc : -INFINITY;
+  float s_hi = (act && j + 8 < npos) ? s[2] * sc : -INFINITY;
+  float mx = fmaxf(s_lo, s_hi);
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+  const float m_new = fmaxf(st.m, mx);
+  const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+  const float corr = exp2f(st.m - m_use);
+  st.m = m_new;
+  const float p_lo = exp2f(s_lo - m_use), p_hi = exp2f(s_hi - m_use);
+  st.l = st.l * corr + p_lo + p_hi;
+  // p as the B operand (k = position, column 0): lanes 0-3 need p[2l], p[2l+1], p[2l+8], p[2l+9]
+  const int src = 8 * (lane & 3);
+  const float x0 = __shfl_sync(0xffffffffu, p_lo, src), x1 = __shfl_sync(0xffffffffu, p_lo, src + 4);
+  const float y0 = __shfl_sync(0xffffffffu, p_hi, src), y1 = __shfl_sync(0xffffffffu, p_hi, src + 4);
+  const uint32_t b0 = (lane < 4) ? pack_bf16(x0, x1) : 0u;
+  const uint32_t b1 = (lane < 4) ? pack_bf16(y0, y1) : 0u;
+  const int vpos = r + 8 * (mi >> 1);                     // V (transposed read): matrices 0/1 rows 0-7, 2/3 rows 8-15
+#pragma unroll
+  for (int db = 0; db < 4; ++db) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) st.acc[db][i] *= corr;
+    uint32_t a0, a1, a2, a3;
+    const int ch = db * 2 + (mi & 1);
+    ldsm_x4_t(vt + vpos * 128 + ((ch ^ (vpos & 7)) << 4), a0, a1, a2, a3);
+    mma_bf16_16816(st.acc[db], a0, a1, a2, a3, b0, b1);
+  }
+}
+
+TTB_DEVINL void attn_phase_mma(const AsParams& p, int layer, uint8_t* data, AsCtrl* ctrl, AsRole& rl) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* err = &p.state->reserved[0];
+  const int B = p.B, H = p.H, P = p.P, Nmax = p.Nmax, D = p.H * 64;
+  const int NS = p.ring_ns;
+  constexpr int CHUNK_BYTES = 16 * AS_POS_BYTES;       // K tile 2 KB | V tile 2 KB
+  const int slot = p.state->step - 1;
+  const int nold = slot;
+  uint8_t* ring = data + warp * NS * CHUNK_BYTES;
+  uint8_t* prefix_s = data + p.ipr * p.team * NS * CHUNK_BYTES;
+  const CUtensorMap* map_c = p.maps + 4 * p.L + 5;
+  const CUtensorMap* map_p = map_c + 1;
+  __nv_bfloat16* ckv_l = p.cand_kv + (long long)layer * B * H * Nmax * 128;
+  const int npc = (P + 15) / 16;
+  const int units = H * p.ncph;
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const int h = u % H, ci = u / H;
+    const int b_begin = (int)((long long)ci * B / p.ncph), b_end = (int)((long long)(ci + 1) * B / p.ncph);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_arrive_expect_tx(&ctrl->prefix_bar, (uint32_t)(npc * CHUNK_BYTES));
+      for (int c = 0; c < npc; ++c) {
+        tma_load_4d(prefix_s + c * CHUNK_BYTES, map_p, &ctrl->prefix_bar, 0, 0, c * 16, layer * H + h);
+        tma_load_4d(prefix_s + c * CHUNK_BYTES + 2048, map_p, &ctrl->prefix_bar, 0, 1, c * 16, layer * H + h);
+      }
+    }
+    const int sub = warp % p.team;
+    for (int r0 = b_begin; r0 < b_end; r0 += p.ipr) {
+      const int b = r0 + warp / p.team;
+      const bool valid = (warp < p.ipr * p.team) && (b < b_end);
+      MmaState st;
+      st.m = -INFINITY; st.l = 0.f;
+#pragma unroll
+      for (int db = 0; db < 4; ++db)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) st.acc[db][i] = 0.f;
+      if (valid) {
+        const __nv_bfloat16* qrow = p.qkv + (long long)b * 3 * D + h * 64;
+        // q as the B operand of the score MMA: column 0 <-> lanes 0-3; b0 = dims 16 ks + 2 lane (+1), b1 = + 8
+        uint32_t qb[8];
+        const uint32_t* q32 = reinterpret_cast<const uint32_t*>(qrow);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          qb[2 * ks] = (lane < 4) ? __ldcg(q32 + ks * 8 + lane) : 0u;
+          qb[2 * ks + 1] = (lane < 4) ? __ldcg(q32 + ks * 8 + 4 + lane) : 0u;
+        }
+        __nv_bfloat16* cb = ckv_l + ((long long)b * H + h) * Nmax * 128;
+        const int item = (layer * B + b) * H + h;          // 4th coordinate of the candidate-cache tensor map
+        const int nch = (nold + 15) / 16;
+        if (lane == 0) {
+          for (int s = 0; s < NS; ++s) {
+            const int c = sub + s * p.team;
+            if (c < nch) {
+              mbar_arrive_expect_tx(&ctrl->ring_bar[warp][s], (uint32_t)CHUNK_BYTES);
+              tma_load_4d(ring + s * CHUNK_BYTES, map_c, &ctrl->ring_bar[warp][s], 0, 0, c * 16, item);
+              tma_load_4d(ring + s * CHUNK_BYTES + 2048, map_c, &ctrl->ring_bar[warp][s], 0, 1, c * 16, item);
+            }
+          }
+        }
+        if (sub == 0) {
+          // the new token: append K / V to the cache, account for it from registers (SIMT, once per item)
+          const uint32_t kq = __ldcg(reinterpret_cast<const uint32_t*>(qrow + D) + lane);      // dims 2 lane, 2 lane + 1
+          const uint32_t qq = __ldcg(q32 + lane);
+          const float2 kf = unpack_bf16(kq), qf = unpack_bf16(qq);
+          float sn = warp_sum(kf.x * qf.x + kf.y * qf.y) * (0.125f * 1.4426950408889634f);
+          if (lane < 16) {
+            const uint4 nv = __ldcg(reinterpret_cast<const uint4*>(qrow + (lane < 8 ? D : 2 * D)) + (lane & 7));
+            reinterpret_cast<uint4*>(cb + (long long)slot * 128 + (lane < 8 ? 0 : 64))[lane & 7] = nv;
+          }
+          st.m = sn;
+          st.l = (lane == 0) ? 1.f : 0.f;
+          if ((lane & 3) == 0) {
+            const __nv_bfloat16* vrow = qrow + 2 * D;
+            const int j = lane >> 2;
+#pragma unroll
+            for (int db = 0; db < 4; ++db) {
+              st.acc[db][0] = __bfloat162float(vrow[db * 16 + j]);
+              st.acc[db][2] = __bfloat162float(vrow[db * 16 + j + 8]);
+            }
+          }
+        }
+        int s = 0;
+        for (int c_use = sub; c_use < nch; c_use += p.team) {
+          mbar_wait_to(&ctrl->ring_bar[warp][s], rl.ring_par[s], err);
+          rl.ring_par[s] ^= 1;
+          const uint32_t kt = smem_u32(ring + s * CHUNK_BYTES);
+          mma_chunk(st, qb, kt, kt + 2048, min(16, nold - c_use * 16), lane);
+          __syncwarp();
+          const int c_next = c_use + NS * p.team;
+          if (lane == 0 && c_next < nch) {
+            mbar_arrive_expect_tx(&ctrl->ring_bar[warp][s], (uint32_t)CHUNK_BYTES);
+            tma_load_4d(ring + s * CHUNK_BYTES, map_c, &ctrl->ring_bar[warp][s], 0, 0, c_next * 16, item);
+            tma_load_4d(ring + s * CHUNK_BYTES + 2048, map_c, &ctrl->ring_bar[warp][s], 0, 1, c_next * 16, item);
+          }
+          if (++s == NS) s = 0;
+        }
+        mbar_wait_to(&ctrl->prefix_bar, rl.prefix_par, err);
+        for (int c = sub; c < npc; c += p.team) {
+          const uint32_t kt = smem_u32(prefix_s + c * CHUNK_BYTES);
+          mma_chunk(st, qb, kt, kt + 2048, min(16, P - c * 16), lane);
+        }
+        st.l = warp_sum(st.l);
+      }
+      // ---- gather the row: (m, l, O[64]) of this warp into the scratch; leaders merge the team and write o
+      float* ms = ctrl->merge[warp];
+      if (valid) {
+        if ((lane & 3) == 0) {
+          const int j = lane >> 2;
+#pragma unroll
+          for (int db = 0; db < 4; ++db) { ms[db * 16 + j] = st.acc[db][0]; ms[db * 16 + j + 8] = st.acc[db][2]; }
+        }
+        if (lane == 0) { ms[64] = st.m; ms[65] = st.l; }
+      }
+      if (p.team > 1) __syncthreads(); else __syncwarp();
+      if (valid && sub == 0 && lane < 8) {
+        float m = ms[64], l = ms[65];
+        float o[8];
+#pragma unroll
+        for (int d = 0; d < 8; ++d) o[d] = ms[lane * 8 + d];
+        for (int t = 1; t < p.team; ++t) {
+          const float* mo = ctrl->merge[warp + t];
+          const float m_o = mo[64], l_o = mo[65];
+          const float m_new = fmaxf(m, m_o);
+          const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+          const float c_s = exp2f(m - m_use), c_o = exp2f(m_o - m_use);
+          l = l * c_s + l_o * c_o;
+#pragma unroll
+          for (int d = 0; d < 8; ++d) o[d] = o[d] * c_s + mo[lane * 8 + d] * c_o;
+          m = m_new;
+        }
+        const float inv = 1.0f / l;
+        reinterpret_cast<uint4*>(p.o + (long long)b * D + h * 64)[lane] =
+            make_uint4(pack_bf16(o[0] * inv, o[1] * inv), pack_bf16(o[2] * inv, o[3] * inv),
+                       pack_bf16(o[4] * inv, o[5] * inv), pack_bf16(o[6] * inv, o[7] * inv));
+      }
+      if (p.team > 1) __syncthreads(); else __syncwarp();     // scratch is rewritten by the next round
     }
     rl.prefix_par ^= 1;
   }
@@ -722,7 +944,8 @@ __global__ void __launch_bounds__(AS_THREADS, 1) ar_step_kernel(const __grid_con
       AS_SYNC_UNLESS_LAST(1, l);
     }
     if (p.phase_mask & PH_ATTN) {
-      if (p.ring_cp == 8) attn_phase<8>(p, l, data, ctrl, rl);
+      if (p.attn_impl == 1) attn_phase_mma(p, l, data, ctrl, rl);
+      else if (p.ring_cp == 8) attn_phase<8>(p, l, data, ctrl, rl);
       else attn_phase<16>(p, l, data, ctrl, rl);
       AS_SYNC_UNLESS_LAST(2, l);
     }
@@ -772,6 +995,30 @@ __global__ void __launch_bounds__(AS_THREADS, 1) ar_step_kernel(const __grid_con
     // every CTA has read the epoch before its first arrival, and all arrivals of this launch precede this point
     *reinterpret_cast<volatile unsigned long long*>(p.bar) = rl.bar_target;
   }
+}
+
+// The attention phase alone as an ordinary (non-cooperative) launch: no TMEM, no grid barrier. Used by the "mixed" decode
+// mode, where the GEMMs / LayerNorms of the step stay separate kernels (faster at >= 64 candidates, see ar_engine.py).
+__global__ void __launch_bounds__(AS_THREADS, 1) ar_attn_only_kernel(const __grid_constant__ AsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* data = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  AsCtrl* ctrl = reinterpret_cast<AsCtrl*>(data + AS_DATA_BYTES);
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < AS_WARPS; ++w)
+      for (int k = 0; k < 4; ++k) mbar_init(&ctrl->ring_bar[w][k], 1);
+    mbar_init(&ctrl->prefix_bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  pdl_wait();                      // qkv belongs to the c_attn GEMM before this point (TTB_PDL=1)
+  AsRole rl;
+  rl.stage = 0; rl.phase = 0; rl.acc_par = 0; rl.prefix_par = 0; rl.bar_target = 0;
+  rl.ring_par[0] = rl.ring_par[1] = rl.ring_par[2] = rl.ring_par[3] = 0;
+  const int l = p.layer_begin;
+  if (p.attn_impl == 1) attn_phase_mma(p, l, data, ctrl, rl);
+  else if (p.ring_cp == 8) attn_phase<8>(p, l, data, ctrl, rl);
+  else attn_phase<16>(p, l, data, ctrl, rl);
+  pdl_launch_dependents();
 }
 
 // prompt K/V from a qkv buffer [P, 3*H*64] into the interleaved prefix cache [H][P][K 64 | V 64]
@@ -855,24 +1102,32 @@ static int make_plan(const TtbArStepArgs& a, AsPlan& pl) {
   if (p.ncph < 1) p.ncph = 1;
   if (p.ncph > a.B) p.ncph = a.B;
   const int max_items = (a.B + p.ncph - 1) / p.ncph;
-  const int rounds = (max_items + AS_WARPS - 1) / AS_WARPS;
+  int wcap = env_int("TTB_AR_STEP_ATTN_WARPS", AS_WARPS);      // experiments: fewer concurrent streams, deeper rings
+  if (wcap < 1 || wcap > AS_WARPS) wcap = AS_WARPS;
+  const int rounds = (max_items + wcap - 1) / wcap;
   p.ipr = (max_items + rounds - 1) / rounds;
   int team = 1;
-  while (team * 2 * p.ipr <= AS_WARPS) team *= 2;
+  while (team * 2 * p.ipr <= wcap) team *= 2;
   const int tcap = env_int("TTB_AR_STEP_TEAM", 0);
   if (tcap > 0 && tcap < team) team = tcap;
   p.team = team;
   p.prefetch = env_int("TTB_AR_STEP_PREFETCH", 1);
   p.sync_mode = env_int("TTB_AR_STEP_SYNC", 1);
-  p.ring_cp = env_int("TTB_AR_STEP_RING_CP", 16) == 8 ? 8 : 16;
+  p.attn_impl = env_int("TTB_AR_STEP_ATTN_MMA", 1) ? 1 : 0;
+  p.ring_cp = (env_int("TTB_AR_STEP_RING_CP", 16) == 8 && !p.attn_impl) ? 8 : 16;
   p.ring_ns = env_int("TTB_AR_STEP_RING_NS", 2);
   if (p.ring_ns < 2) p.ring_ns = 2;
   if (p.ring_ns > 4) p.ring_ns = 4;
-  // the rings of all warps + the prompt prefix of one head share the data region
-  while (p.ring_ns > 2 && AS_WARPS * p.ring_ns * p.ring_cp * AS_POS_BYTES + ((a.P + 15) & ~15) * AS_POS_BYTES > AS_DATA_BYTES) --p.ring_ns;
-  if (AS_WARPS * p.ring_ns * p.ring_cp * AS_POS_BYTES + ((a.P + 15) & ~15) * AS_POS_BYTES > AS_DATA_BYTES) {
-    set_error("ttb_ar_step: ring %d x %d positions + prompt %d do not fit shared memory", p.ring_ns, p.ring_cp, a.P);
-    return -1;
+  // the rings of the active warps + the prompt prefix of one head share the data region
+  {
+    const int nact = p.ipr * p.team;
+    const long long pref = (long long)((a.P + 15) & ~15) * AS_POS_BYTES;
+    while (p.ring_ns > 2 && (long long)nact * p.ring_ns * p.ring_cp * AS_POS_BYTES + pref > AS_DATA_BYTES) --p.ring_ns;
+    if ((long long)nact * p.ring_ns * p.ring_cp * AS_POS_BYTES + pref > AS_DATA_BYTES) {
+      set_error("ttb_ar_step: ring %d x %d positions x %d warps + prompt %d do not fit shared memory", p.ring_ns, p.ring_cp,
+                nact, a.P);
+      return -1;
+    }
   }
   p.layer_begin = 0; p.layer_end = a.L; p.phase_mask = 0x1ff;
   if (a.debug_layer_end > 0) { p.layer_begin = a.debug_layer_begin; p.layer_end = a.debug_layer_end; }
@@ -882,8 +1137,9 @@ static int make_plan(const TtbArStepArgs& a, AsPlan& pl) {
   return 0;
 }
 
+constexpr int AS_EXTRA_MAPS = 6;      // activations a, o, h, hn; candidate KV cache; prompt-prefix KV cache
 static long long table_bytes(int L) {
-  return (long long)(4 * L + 1 + 4) * sizeof(CUtensorMap) + (long long)L * sizeof(AsLayer) + 256;
+  return (long long)(4 * L + 1 + AS_EXTRA_MAPS) * sizeof(CUtensorMap) + (long long)L * sizeof(AsLayer) + 256;
 }
 
 }  // namespace ttb
@@ -907,7 +1163,7 @@ extern "C" int ttb_ar_step_setup(const TtbArStepArgs* ap, void* stream) {
   AsPlan pl;
   if (make_plan(a, pl)) return -1;
   if (!a.layers || !a.tables || !a.sync) { set_error("ttb_ar_step_setup: missing tables"); return -1; }
-  const int nmaps = 4 * a.L + 1 + 4;
+  const int nmaps = 4 * a.L + 1 + AS_EXTRA_MAPS;
   std::vector<unsigned char> host((size_t)table_bytes(a.L), 0);
   CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(host.data());
   AsLayer* lay = reinterpret_cast<AsLayer*>(host.data() + (size_t)nmaps * sizeof(CUtensorMap));
@@ -929,6 +1185,16 @@ extern "C" int ttb_ar_step_setup(const TtbArStepArgs* ap, void* stream) {
   if (get_tensor_map_bf16(&am[1], a.o, D, Bq, 1, D, Bq * D, 64, TB)) return -1;
   if (get_tensor_map_bf16(&am[2], a.h, 4 * D, Bq, 1, 4 * D, Bq * 4 * D, 64, TB)) return -1;
   if (get_tensor_map_bf16(&am[3], a.hn, D, Bq, 1, D, Bq * D, 64, TB)) return -1;
+  {
+    // KV caches as 4-D tensors [item][position][K|V][64]: one box = 16 positions of K (or V) of one (layer, cand, head)
+    const uint32_t box[4] = {64, 1, 16, 1};
+    const uint64_t cd[4] = {64, 2, (uint64_t)a.Nmax, (uint64_t)a.L * a.B * a.H};
+    const uint64_t cs[3] = {128, 256, (uint64_t)a.Nmax * 256};
+    if (make_tensor_map_bf16_nd(&am[4], a.cand_kv, 4, cd, cs, box)) return -1;
+    const uint64_t pd[4] = {64, 2, (uint64_t)a.P, (uint64_t)a.L * a.H};
+    const uint64_t ps[3] = {128, 256, (uint64_t)a.P * 256};
+    if (make_tensor_map_bf16_nd(&am[5], a.prefix_kv, 4, pd, ps, box)) return -1;
+  }
   cudaError_t e = cudaMemcpyAsync(a.tables, host.data(), host.size(), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(a.sync, 0, AS_SYNC_BAR_BYTES + AS_MAX_TILES * 4, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -936,6 +1202,7 @@ extern "C" int ttb_ar_step_setup(const TtbArStepArgs* ap, void* stream) {
   static bool attr_set = false;
   if (!attr_set) {
     e = cudaFuncSetAttribute(ar_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AS_SMEM_TOTAL);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ar_attn_only_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AS_SMEM_TOTAL);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(ar_step_kernel)");
     attr_set = true;
   }
@@ -948,7 +1215,7 @@ extern "C" int ttb_ar_decode_step(const TtbArStepArgs* ap, void* stream) {
   AsPlan pl;
   if (make_plan(a, pl)) return -1;
   AsParams& p = pl.p;
-  const int nmaps = 4 * a.L + 1 + 4;
+  const int nmaps = 4 * a.L + 1 + AS_EXTRA_MAPS;
   p.maps = reinterpret_cast<const CUtensorMap*>(a.tables);
   p.layers = reinterpret_cast<const AsLayer*>(reinterpret_cast<const unsigned char*>(a.tables) + (size_t)nmaps * sizeof(CUtensorMap));
   p.lnf_g = a.lnf_g; p.lnf_b = a.lnf_b; p.fn_g = a.fn_g; p.fn_b = a.fn_b; p.b_head = a.b_head;
@@ -962,6 +1229,14 @@ extern "C" int ttb_ar_decode_step(const TtbArStepArgs* ap, void* stream) {
   p.cand_kv = reinterpret_cast<__nv_bfloat16*>(a.cand_kv);
   p.bar = reinterpret_cast<unsigned long long*>(a.sync);
   p.tickets = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(a.sync) + AS_SYNC_BAR_BYTES);
+  if (p.phase_mask == PH_ATTN && p.layer_end == p.layer_begin + 1) {
+    const int units = a.H * p.ncph;
+    const cudaError_t la = launch_pdl(ar_attn_only_kernel, dim3(units < pl.grid ? units : pl.grid), dim3(AS_THREADS),
+                                      (size_t)AS_SMEM_TOTAL, st, p);
+    if (la != cudaSuccess) return check_cuda(la, "ar_attn_only_kernel launch");
+    TTB_CHECK_LAUNCH("ar_attn_only_kernel");
+    return 0;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pl.grid);
   cfg.blockDim = dim3(AS_THREADS);

@@ -198,7 +198,6 @@ ar_decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16
                       const __nv_bfloat16* __restrict__ pv, __nv_bfloat16* __restrict__ ck,
                       __nv_bfloat16* __restrict__ cv, const TtbArState* __restrict__ state, int B, int H, int P, int Nmax,
                       float* __restrict__ o_c, float* __restrict__ lse_c) {
-  pdl_launch_dependents();
   pdl_wait();
   const int h = blockIdx.x;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -312,7 +311,6 @@ ar_decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16
 __global__ void ar_attn_merge_kernel(const float* __restrict__ o_p, const float* __restrict__ lse_p,
                                      const float* __restrict__ o_c, const float* __restrict__ lse_c, int B, int H,
                                      __nv_bfloat16* __restrict__ out) {
-  pdl_launch_dependents();
   pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over B * H * 16 (4 dims each)
   if (i >= (long long)B * H * 16) return;

@@ -27,11 +27,11 @@ int check_cuda(cudaError_t e, const char* what);
 // cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs are scheduled, run their prologue
 // (barrier init, TMEM allocation, descriptor prefetch) and park in griddepcontrol.wait while the previous kernel
 // drains, which removes the kernel-to-kernel launch gap that dominates the ~10 us decode-step kernels.
-// Measured in round 1 (profiles/bench_r01_pdl.txt): TTB_PDL=1 is correct (GPU parity tests pass, CUDA-graph capture of
-// the programmatic edges works) but SLOWER, AR 1346 -> 1445 ms: with the trigger at the very top of every kernel the
-// dependent's CTAs become resident at once and take registers / shared memory away from the kernel that is still
-// running (the decode-attention kernel loses occupancy). Hence off by default; next step is to move the trigger to each
-// kernel's tail (after its main loop) so that only launch latency and prologue overlap.
+// Round 1 (profiles/bench_r01_pdl.txt): with the trigger at the very TOP of every kernel PDL was correct but slower
+// (AR 1346 -> 1445 ms): the dependent's CTAs became resident at once and took registers / shared memory away from the
+// kernel still running. Round 2 moved every trigger to the kernel's TAIL (GEMM: once all loads of the CTA are issued and
+// its accumulator is complete; LayerNorm: after its loads; others: at exit): AR 1246 -> 1187 ms with TTB_PDL=1
+// (gpurun_out/r2e, profiles/bench_r02_*.json). On by default; TTB_PDL=0 restores plain launches.
 TTB_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 TTB_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -39,7 +39,7 @@ inline bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("TTB_PDL");
-    v = (e && e[0] == '1') ? 1 : 0;
+    v = (e && e[0] == '0') ? 0 : 1;       // default on since round 2 (triggers at the kernel tails)
   }
   return v == 1;
 }

@@ -55,8 +55,8 @@ TTB_DEVINL float exp2_poly(float x) {
 
 template <bool POLY>
 __global__ void __launch_bounds__(F2_THREADS, 1)
-flash_attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, TtbAttnArgs a) {
-  pdl_launch_dependents();
+flash_attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, TtbAttnArgs a,
+                   int turns) {
   pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -185,8 +185,21 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const uint32_t tmem_o = tmem_base + 128 + g * 64 + ((uint32_t)(qd * 32) << 16);
     uint8_t* sp = smem + F2Smem::P_OFF + g * F2Smem::P_BYTES;
     const int bar_id = 1 + g;
+    // Softmax turn-taking (named barriers 3 / 4, 256 threads = both warpgroups): without it the two warpgroups run in
+    // phase - both do their softmax at the same time, fighting for the issue slots and the exponent unit, then both wait
+    // for the tensor core - and the kernel is no faster than one tile per CTA (measured: 0.110 ms either way). With it,
+    // group B's softmax of tile j runs while group A waits for S_A(j+1) and vice versa.
+    const int my_turn = 3 + g, other_turn = 4 - g;
+    if (turns && g == 1) asm volatile("bar.arrive %0, 256;" ::"r"(3) : "memory");      // group A goes first
     float m = -INFINITY, l = 0.f;
-    for (int j = 0; j < nt; ++j) {
+    for (int j = 0; j < ntiles; ++j) {
+      if (j >= nt) {                         // this group has no tile j (causal: fewer key tiles; tile B out of range)
+        if (turns) {
+          asm volatile("bar.sync %0, 256;" ::"r"(my_turn) : "memory");
+          asm volatile("bar.arrive %0, 256;" ::"r"(other_turn) : "memory");
+        }
+        continue;
+      }
       const int k0 = j * F2_BN;
       // tile classes (uniform over the warpgroup): far from the diagonal the T5 bias is constant over the tile
       // (buckets saturate at max_distance) and no key is masked -> one FFMA + one EX2 per score
@@ -209,6 +222,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       }
       // S(j) complete; the commit behind it also covers P V(j-1): O and the P buffer are free
       mbar_wait(&s_full[g], j & 1);
+      if (turns) asm volatile("bar.sync %0, 256;" ::"r"(my_turn) : "memory");
       tc_fence_after();
       uint32_t r0[32], r1[32];
       tmem_ld_32x32b_x32(tmem_s, r0);
@@ -284,7 +298,10 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&p_full[g]);
+      if (turns) asm volatile("bar.arrive %0, 256;" ::"r"(other_turn) : "memory");
     }
+    // balance the last arrive of the other group (every bar.arrive needs its bar.sync before the barrier id is reused)
+    if (turns && g == 0) asm volatile("bar.sync %0, 256;" ::"r"(3) : "memory");
     if (nt > 0) {
       mbar_wait(&o_full[g], (nt - 1) & 1);
       tc_fence_after();
@@ -312,6 +329,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       }
     }
   }
+  pdl_launch_dependents();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -321,7 +339,12 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 
 bool flash_attention2_supported(const TtbAttnArgs& a) {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("TTB_FA2"); on = (e && e[0] == '0') ? 0 : 1; }
+  // Measured on B200 at 2 x 16 heads, S = 1872 (tools/dbg/fa_time.py): one-tile kernel 0.109 ms, + double-buffered scores
+  // (TTB_FA_DBUF, default) 0.098 ms; this kernel 0.102 ms (0.111 with the polynomial exp2 share, 0.121 with softmax
+  // turn-taking): no gain from the ping-pong form - two co-resident CTAs of the one-tile kernel already interleave two
+  // tiles per SM, and the softmax warps are bound by their own dependent chains (ncu: issue 39 %, XU 36 %, tensor 15 %).
+  // Kept selectable (TTB_FA2=1) and tested; not the default.
+  if (on < 0) { const char* e = getenv("TTB_FA2"); on = (e && e[0] == '1') ? 1 : 0; }
   if (!on) return false;
   if (a.kv || a.lse || a.out_f32) return false;       // partial-attention form stays with flash_attn.cu
   if (a.Tk > 0 && a.Tk != a.T) return false;
@@ -334,8 +357,9 @@ int flash_attention2_launch(const TtbAttnArgs& a, cudaStream_t st) {
                           (uint64_t)a.T * a.ld, 64, F2_BM)) return -1;
   if (get_tensor_map_bf16(&mkv, a.qkv, (uint64_t)a.ld, (uint64_t)a.T, (uint64_t)a.nseq, (uint64_t)a.ld,
                           (uint64_t)a.T * a.ld, 64, F2_BN)) return -1;
-  static int poly = -1;
-  if (poly < 0) { const char* e = getenv("TTB_FA2_POLY"); poly = (e && e[0] == '0') ? 0 : 1; }
+  static int poly = -1, turns = -1;
+  if (poly < 0) { const char* e = getenv("TTB_FA2_POLY"); poly = (e && e[0] == '1') ? 1 : 0; }
+  if (turns < 0) { const char* e = getenv("TTB_FA2_TURNS"); turns = (e && e[0] == '1') ? 1 : 0; }
   static bool attr = false;
   if (!attr) {
     cudaError_t r = cudaFuncSetAttribute(flash_attn2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2Smem::TOTAL);
@@ -344,8 +368,8 @@ int flash_attention2_launch(const TtbAttnArgs& a, cudaStream_t st) {
     attr = true;
   }
   dim3 grid((a.T + 2 * F2_BM - 1) / (2 * F2_BM), a.H, a.nseq);
-  const cudaError_t le = poly ? launch_pdl(flash_attn2_kernel<true>, grid, dim3(F2_THREADS), (size_t)F2Smem::TOTAL, st, mq, mkv, a)
-                              : launch_pdl(flash_attn2_kernel<false>, grid, dim3(F2_THREADS), (size_t)F2Smem::TOTAL, st, mq, mkv, a);
+  const cudaError_t le = poly ? launch_pdl(flash_attn2_kernel<true>, grid, dim3(F2_THREADS), (size_t)F2Smem::TOTAL, st, mq, mkv, a, turns)
+                              : launch_pdl(flash_attn2_kernel<false>, grid, dim3(F2_THREADS), (size_t)F2Smem::TOTAL, st, mq, mkv, a, turns);
   if (le != cudaSuccess) return check_cuda(le, "flash_attn2_kernel launch");
   TTB_CHECK_LAUNCH("flash_attn2_kernel");
   return 0;

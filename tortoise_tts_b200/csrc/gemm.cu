@@ -87,6 +87,23 @@ int get_tensor_map_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t
   return 0;
 }
 
+// General form: bf16, rank <= 5, explicit byte strides of dims 1.. (dim 0 contiguous), SWIZZLE_128B (box[0] * 2 == 128).
+int make_tensor_map_bf16_nd(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                            const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return -1; }
+  cuuint64_t d[5];
+  cuuint64_t st[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), d, st, b, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (rank %d) failed (%d)", rank, (int)r); return -1; }
+  return 0;
+}
+
 // ------------------------------------------------------------------ kernel
 constexpr int BM = 128;
 constexpr int BK = 64;
@@ -130,7 +147,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   // optional per-CTA phase timestamps (ttb_debug_gemm_trace): 8 x u64 per CTA, see tools/gemm_diag.py
   unsigned long long* tr = trace ? trace + 8ull * (blockIdx.x + gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z)) : nullptr;
   if (tr && threadIdx.x == 0) { tr[0] = global_timer_ns(); tr[1] = sm_id(); }
-  pdl_launch_dependents();
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* accum_bar = empty_bar + STAGES;
@@ -184,6 +200,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    pdl_launch_dependents();      // PDL trigger at the TAIL (round 1 had it at the top and lost 7 %): the dependents'
+                                  // CTAs may be scheduled once every CTA of this grid has all its loads in flight
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
@@ -207,6 +225,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       umma_commit(accum_bar);
       if (tr) tr[4] = global_timer_ns();
     }
+    pdl_launch_dependents();
   } else {
     // ===== epilogue: warps 2..5; warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
     const int q = warp & 3;
@@ -237,6 +256,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
     }
     mbar_wait(accum_bar, 0);
+    pdl_launch_dependents();
     tc_fence_after();
     if (tr && threadIdx.x == 64) tr[5] = global_timer_ns();
     // all MMAs have retired: the pipeline stages are idle and serve as the per-warp transpose scratch

@@ -38,7 +38,6 @@ gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const 
   uint64_t* acc_empty = acc_full + 2;           // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int kblocks_per_tap = K / BK;
@@ -128,6 +127,7 @@ gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const 
                                   smem_u32(smem + L::SCRATCH_OFF + (warp - 2) * EPI_SCRATCH_BYTES), &acc_empty[acc]);
     }
   }
+  pdl_launch_dependents();      // tail trigger (see gemm.cu)
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();

@@ -84,7 +84,6 @@ layernorm_warp_kernel(const float* x, int M, int D, const float* __restrict__ g1
                       const float* __restrict__ g2, const float* __restrict__ b2, __nv_bfloat16* __restrict__ ob,
                       float* __restrict__ of, float* xw, const float* __restrict__ partials, int nsplit,
                       long long split_stride, const float* __restrict__ rbias) {
-  pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 2 + (threadIdx.x >> 5);
@@ -112,6 +111,7 @@ layernorm_warp_kernel(const float* x, int M, int D, const float* __restrict__ g1
       *reinterpret_cast<float4*>(xw + row * D + (i * 32 + lane) * 4) = v[i];
     }
   }
+  pdl_launch_dependents();        // tail trigger: every load of this row is done
 #pragma unroll
   for (int pass = 0; pass < 2; ++pass) {
     const float* gg = pass == 0 ? g1 : g2;
@@ -261,8 +261,7 @@ gn_apply_kernel(const float* __restrict__ x, int S, int C, int groups, int cpg, 
 __global__ void __launch_bounds__(256)
 gn_stats_rows_kernel(const float* __restrict__ x, int B, int S, int C, int groups, int cpg, int tpr, int rows_per,
                      int splits, float* __restrict__ scratch) {
-  pdl_launch_dependents();
-  pdl_wait();
+  pdl_wait();       // (no early PDL trigger: the dependents are scheduled when this grid drains)
   __shared__ float sacc[2 * 256];                               // [row lane][group][2]; rows_par * groups = 256 / lpg
   const int sp = blockIdx.x, b = blockIdx.y;
   const int rows_par = 256 / tpr;
@@ -312,7 +311,6 @@ gn_apply_rows_kernel(const float* __restrict__ x, int S, int C, int groups, int 
                      const float* __restrict__ scratch, const float* __restrict__ gamma, const float* __restrict__ beta,
                      const float* __restrict__ ss, int ss_bstride, const int* __restrict__ ss_row, int ss_row_stride,
                      int do_silu, __nv_bfloat16* __restrict__ ob, int ldo, float* __restrict__ of, int ldof) {
-  pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.y;
   const int rows_par = 256 / tpr;
