@@ -216,11 +216,22 @@ typedef struct TtbDiffStepArgs {
   int S, C, iters;
   int cond_free; float cond_free_k;
   float* mel_out;           /* optional fp32 [C, S] channel-major denormalised mel written when i == 0 */
+  long long parity_stride;  /* != 0: model_out is the double-buffered exchange area of ttb_pair_exchange; this call reads
+                               model_out + (call & 1) * parity_stride */
 } TtbDiffStepArgs;
 /* p_mean_variance + p_sample epilogue (utils/diffusion.py:340-418,487-531): CFG mix with linear ramp,
  * learned-range variance, eps->x0 clamp, posterior mean, ancestral noise; denormalize_tacotron_mel on the
  * last step (utils/audio.py:63-64). */
 int ttb_diffusion_step(const TtbDiffStepArgs* args, void* stream);
+/* CFG branch pair on two GPUs (no reference counterpart: the reference runs both branches on one device,
+ * utils/diffusion.py:340-342): copies this rank's branch output `src` (n floats) into slot (call & 1, branch_off) of the
+ * local AND the partner's exchange area (peer memory mapped through CUDA IPC), publishes epoch + call + 1 in the
+ * partner's flag word of that parity and waits for the partner's. One launch, CUDA-graph capturable. *err is set to 1
+ * if the partner does not answer within 5 s. */
+int ttb_pair_exchange(const float* src, float* local_area, float* peer_area, long long n, long long parity_stride,
+                      long long branch_off, int* peer_flags, int* my_flags, const int* counter, const int* epoch,
+                      unsigned int* done_ctr, int* err, void* stream);
+int ttb_enable_peer_access(int peer_device);
 /* misc small device helpers */
 int ttb_counter_add(int* counter, int delta, void* stream);
 int ttb_transpose_f32(const float* in, int R, int Cc, float* out, void* stream);           /* [R, C] -> [C, R] */

@@ -300,7 +300,8 @@ def interp_nearest(x, N, S, Cc, out_bf16=None, ldo=0, out_f32=None, ldof=0):
 
 
 def diffusion_step(model_out, out_bstride, ld_out, x, x_bf16, ld_xb, noise, tables, step, S, Cc, iters, cond_free,
-                   cond_free_k, mel_out=None):
+                   cond_free_k, mel_out=None, parity_stride=0):
+    assert parity_stride == 0, "the peer-exchange area exists on GPUs only"
     call = int(step[0])
     i = iters - 1 - call
     tb = _v(tables, (6, iters), (iters, 1))

@@ -149,11 +149,13 @@ diffusion_step_kernel(TtbDiffStepArgs a) {
   const float* tb = a.tables;
   const float sra = tb[0 * a.iters + i], srm1 = tb[1 * a.iters + i], minlog = tb[2 * a.iters + i],
               maxlog = tb[3 * a.iters + i], c1 = tb[4 * a.iters + i], c2 = tb[5 * a.iters + i];
-  const float* mo = a.model_out + (long long)s * a.ld_out;
+  // parity_stride != 0: the two CFG branches arrive through the double-buffered peer-exchange area (ttb_pair_exchange)
+  const float* mob = a.model_out + (long long)(call & 1) * a.parity_stride;
+  const float* mo = mob + (long long)s * a.ld_out;
   float eps = mo[c];
   const float var = mo[a.C + c];
   if (a.cond_free) {
-    const float eps_u = a.model_out[a.out_bstride + (long long)s * a.ld_out + c];
+    const float eps_u = mob[a.out_bstride + (long long)s * a.ld_out + c];
     // cfk = k * (1 - i / iters)  (utils/diffusion.py:377-383), computed in double as Python does, then fp32 math
     const double cfkd = (double)a.cond_free_k * (1.0 - (double)i / (double)a.iters);
     eps = (float)(1.0 + cfkd) * eps - (float)cfkd * eps_u;
@@ -176,6 +178,42 @@ diffusion_step_kernel(TtbDiffStepArgs a) {
 }
 
 __global__ void counter_add_kernel(int* c, int d) { *c += d; }
+
+// ------------------------------------------------------------------ CFG pair: exchange of the two denoiser branches
+// Two GPUs evaluate one classifier-free-guidance branch each (diffusion_engine.py). Round 1 exchanged the [S, 200] fp32
+// outputs with an eager NCCL all-gather between two CUDA graphs per step (2.55 ms per step against 1.9 ms of compute).
+// This kernel is the exchange as ONE graph-capturable launch over peer memory (CUDA IPC mapping of the partner's buffer,
+// NVLink stores): copy my branch into slot (step parity, my branch) of BOTH exchange areas, publish a flag in the
+// partner's memory, wait for the partner's flag. Slots are double-buffered by step parity: the partner can be at most one
+// step ahead (it needs my data of its current step), so it never overwrites a slot I still read.
+__global__ void __launch_bounds__(256)
+pair_exchange_kernel(const float4* __restrict__ src, float4* __restrict__ local_area, float4* __restrict__ peer_area,
+                     long long n4, long long parity_stride4, long long branch_off4, int* peer_flags, int* my_flags,
+                     const int* __restrict__ counter, const int* __restrict__ epoch, unsigned int* done_ctr, int* err) {
+  const int call = *counter;
+  const int want = *epoch + call + 1;
+  const long long off = (long long)(call & 1) * parity_stride4 + branch_off4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+    local_area[off + i] = v;
+    peer_area[off + i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(done_ctr, 1u);
+    if (t == gridDim.x - 1) {                       // last CTA: every store of this launch is visible system-wide
+      *done_ctr = 0;
+      asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(peer_flags + (call & 1)), "r"(want) : "memory");
+      const unsigned long long t0 = global_timer_ns();
+      int seen;
+      do {
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(my_flags + (call & 1)) : "memory");
+        if (seen - want < 0 && global_timer_ns() - t0 > 5000000000ull) { *err = 1; break; }   // 5 s: partner is gone
+      } while (seen - want < 0);
+    }
+  }
+}
 
 __global__ void transpose_f32_kernel(const float* __restrict__ in, int R, int C, float* __restrict__ out) {
   __shared__ float tile[32][33];
@@ -252,6 +290,28 @@ extern "C" int ttb_diffusion_step(const TtbDiffStepArgs* args, void* stream) {
   const long long n = (long long)args->S * args->C;
   diffusion_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST>>>(*args);
   TTB_CHECK_LAUNCH("diffusion_step_kernel");
+  return 0;
+}
+extern "C" int ttb_pair_exchange(const float* src, float* local_area, float* peer_area, long long n, long long parity_stride,
+                                 long long branch_off, int* peer_flags, int* my_flags, const int* counter, const int* epoch,
+                                 unsigned int* done_ctr, int* err, void* stream) {
+  if ((n & 3) || (parity_stride & 3) || (branch_off & 3)) { set_error("ttb_pair_exchange: sizes must be multiples of 4 floats"); return -1; }
+  pair_exchange_kernel<<<64, 256, 0, ST>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(local_area),
+                                           reinterpret_cast<float4*>(peer_area), n / 4, parity_stride / 4, branch_off / 4,
+                                           peer_flags, my_flags, counter, epoch, done_ctr, err);
+  TTB_CHECK_LAUNCH("pair_exchange_kernel");
+  return 0;
+}
+extern "C" int ttb_enable_peer_access(int peer_device) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (peer_device == dev) return 0;
+  int can = 0;
+  cudaDeviceCanAccessPeer(&can, dev, peer_device);
+  if (!can) { set_error("ttb_enable_peer_access: device %d cannot access device %d", dev, peer_device); return -1; }
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return check_cuda(e, "cudaDeviceEnablePeerAccess");
+  cudaGetLastError();
   return 0;
 }
 extern "C" int ttb_counter_add(int* counter, int delta, void* stream) {

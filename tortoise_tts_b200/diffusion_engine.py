@@ -250,6 +250,18 @@ class DiffusionEngine:
         self._epilogue(st)
 
     def _epilogue(self, st):
+        xch = st.get("xch")
+        if xch is not None:
+            # CFG pair over peer memory: one captured launch puts my branch into both exchange areas and waits for the
+            # partner's (csrc/misc.cu pair_exchange_kernel); the scheduler epilogue then reads the slot of this step's parity
+            n = st["S"] * self.cout
+            lib.pair_exchange(st["mo_local"], xch.area, xch.peer_area, n, 2 * n, xch.my_idx * n, xch.peer_flags, xch.flags,
+                              st["counter"], xch.epoch, xch.done, xch.err)
+            lib.diffusion_step(xch.area, n, self.cout, st["x"], st["x_bf"], self.cin_pad, st["noise"], st["tables"],
+                               st["counter"], st["S"], self.cin, st["iters"], st["cond_free"], st["cond_free_k"], st["mel"],
+                               parity_stride=2 * n)
+            lib.counter_add(st["counter"], 1)
+            return
         if st.get("pair") is not None:
             # CFG pair split over 2 GPUs: this rank evaluated ONE branch (rank 0 of the pair = conditional, rank 1 =
             # unconditional); one all-gather of the [S, 200] fp32 outputs (1.5 MB over NVLink) gives both ranks both
@@ -289,6 +301,11 @@ class DiffusionEngine:
         # current call with the device-side counter, so one captured graph serves every step
         st["ss_all"] = torch.empty(len(self.res_all), iters, 2 * C, dtype=torch.float32, device=dev)
         st["graph"] = None
+        st["xch"] = None
+        if pair is not None and st["model_out"].is_cuda:
+            from . import parallel
+            xch = parallel.PairExchange(pair[0], pair[1], S * self.cout, dev)
+            st["xch"] = xch if xch.ok else None
         self._ws = st
         return st
 
@@ -361,14 +378,18 @@ class DiffusionEngine:
         # The CUDA graph holds the denoiser evaluation (+ the scheduler epilogue when both CFG branches are local).
         # In pair mode the NCCL all-gather is NOT captured (a capture attempt of torch.distributed collectives dead-locked
         # on the GPU box in round 1): graph(forward of my branch) -> eager all-gather -> eager epilogue, per step.
+        fused_epilogue = pair is None or st.get("xch") is not None      # the exchange itself is capturable
+        if st.get("xch") is not None:
+            st["xch"].new_sample()
+
         def captured():
-            if pair is None:
+            if fused_epilogue:
                 self._step(st)
             else:
                 self._forward(st)
 
         def after():
-            if pair is not None:
+            if not fused_epilogue:
                 self._epilogue(st)
 
         def rewind():
@@ -381,6 +402,8 @@ class DiffusionEngine:
                 after()
                 torch.cuda.synchronize()
                 rewind()
+                if st.get("xch") is not None:
+                    st["xch"].new_sample()          # the warm-up step left flags of this epoch behind
                 g = torch.cuda.CUDAGraph()
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
@@ -402,5 +425,7 @@ class DiffusionEngine:
                 after()
                 if return_trace:
                     trace.append(st["x"].t().contiguous().clone())
+        if st.get("xch") is not None and int(st["xch"].err.item()):
+            raise lib.TtbError("CFG pair exchange: the partner rank did not answer within 5 s")
         mel = st["mel"].clone()
         return (mel, trace) if return_trace else mel

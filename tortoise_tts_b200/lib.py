@@ -42,7 +42,7 @@ class DiffStepArgs(C.Structure):
                 ("x", C.c_void_p), ("x_bf16", C.c_void_p), ("ld_xb", C.c_int),
                 ("noise", C.c_void_p), ("tables", C.c_void_p), ("step", C.c_void_p),
                 ("S", C.c_int), ("C", C.c_int), ("iters", C.c_int),
-                ("cond_free", C.c_int), ("cond_free_k", C.c_float), ("mel_out", C.c_void_p)]
+                ("cond_free", C.c_int), ("cond_free_k", C.c_float), ("mel_out", C.c_void_p), ("parity_stride", C.c_longlong)]
 
 
 class ArStepLayer(C.Structure):
@@ -74,6 +74,7 @@ SYMBOLS = [
     "ttb_voc_lvc_gate", "ttb_voc_to_tokens_bf16", "ttb_debug_gemm_trace",
     "ttb_ar_step_workspace", "ttb_ar_step_setup", "ttb_ar_decode_step", "ttb_ar_step_store_prefix",
     "ttb_audio_resample", "ttb_audio_stft_mel", "ttb_mean_rows", "ttb_equal_linear",
+    "ttb_pair_exchange", "ttb_enable_peer_access",
 ]
 
 
@@ -301,9 +302,21 @@ def interp_nearest(x, N, S, Cc, out_bf16=None, ldo=0, out_f32=None, ldof=0):
          "ttb_interp_nearest")
 
 
+def pair_exchange(src, local_area, peer_area, n, parity_stride, branch_off, peer_flags, my_flags, counter, epoch, done_ctr,
+                  err):
+    _chk(load().ttb_pair_exchange(_p(_f32(src)), _p(_f32(local_area)), _p(_f32(peer_area)), C.c_longlong(n),
+                                  C.c_longlong(parity_stride), C.c_longlong(branch_off), _p(peer_flags), _p(my_flags),
+                                  _p(counter), _p(epoch), _p(done_ctr), _p(err), _stream()), "ttb_pair_exchange")
+
+
+def enable_peer_access(peer_device):
+    _chk(load().ttb_enable_peer_access(int(peer_device)), "ttb_enable_peer_access")
+
+
 def diffusion_step(model_out, out_bstride, ld_out, x, x_bf16, ld_xb, noise, tables, step, S, Cc, iters, cond_free,
-                   cond_free_k, mel_out=None):
+                   cond_free_k, mel_out=None, parity_stride=0):
     a = DiffStepArgs()
+    a.parity_stride = parity_stride
     a.model_out, a.out_bstride, a.ld_out = _f32(model_out).data_ptr(), out_bstride, ld_out
     a.x, a.x_bf16, a.ld_xb = _f32(x).data_ptr(), _p(_bf(x_bf16)).value or 0, ld_xb
     a.noise, a.tables, a.step = _f32(noise).data_ptr(), _f32(tables).data_ptr(), step.data_ptr()

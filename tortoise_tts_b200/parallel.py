@@ -125,3 +125,45 @@ def exchange_utterances(parts, plan, device, dtype=torch.float32):
         dist.broadcast(n, src=owner)
         out.append(broadcast_from_owner(mine, int(n.item()), owner, device, dtype))
     return out
+
+
+class PairExchange:
+    """Exchange area of a CFG rank pair over peer memory (CUDA IPC + NVLink stores), used by `lib.pair_exchange`
+    (csrc/misc.cu) inside the captured denoiser step. Layout of `area`: fp32 [2 step parities][2 branches][n].
+    `ok` is False when the mapping could not be set up on BOTH ranks (the caller then keeps the NCCL all-gather)."""
+
+    def __init__(self, group, my_idx, n, device):
+        import os
+        from torch.multiprocessing.reductions import reduce_tensor, rebuild_cuda_tensor
+        from . import lib
+        self.n, self.my_idx = int(n), int(my_idx)
+        self.area = torch.zeros(2 * 2 * self.n, dtype=torch.float32, device=device)
+        self.flags = torch.zeros(32, dtype=torch.int32, device=device)      # [0:2] written by the partner
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self.done = torch.zeros(1, dtype=torch.int32, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        self.peer_area = self.peer_flags = None
+        ok = os.environ.get("TTB_PEER_EXCHANGE", "1") == "1" and self.area.is_cuda
+        metas = [None, None]
+        try:
+            mine = (reduce_tensor(self.area)[1], reduce_tensor(self.flags)[1]) if ok else None
+        except Exception:           # noqa: BLE001  (e.g. an allocator mode without IPC support)
+            mine, ok = None, False
+        dist.all_gather_object(metas, mine, group=group)
+        peer = metas[1 - self.my_idx]
+        if ok and peer is not None:
+            try:
+                self.peer_area = rebuild_cuda_tensor(*peer[0])
+                self.peer_flags = rebuild_cuda_tensor(*peer[1])
+                lib.enable_peer_access(self.peer_area.device.index)
+            except Exception:       # noqa: BLE001
+                ok = False
+        else:
+            ok = False
+        oks = [None, None]
+        dist.all_gather_object(oks, bool(ok), group=group)
+        self.ok = all(bool(v) for v in oks)
+
+    def new_sample(self):
+        """Both ranks call this once per sampling loop, before its first step: flags of earlier loops become stale."""
+        self.epoch.add_(4096)
