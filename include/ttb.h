@@ -232,6 +232,12 @@ int ttb_pair_exchange(const float* src, float* local_area, float* peer_area, lon
                       long long branch_off, int* peer_flags, int* my_flags, const int* counter, const int* epoch,
                       unsigned int* done_ctr, int* err, void* stream);
 int ttb_enable_peer_access(int peer_device);
+/* exchange buffers for ttb_pair_exchange: own cudaMalloc allocation + its 64-byte CUDA-IPC handle; the partner process maps
+ * it with ttb_peer_open (call with ITS device current: peer access is enabled for the mapping) */
+int ttb_peer_alloc(long long bytes, void** ptr, void* handle64);
+int ttb_peer_open(const void* handle64, void** ptr);
+int ttb_peer_close(void* ptr);
+int ttb_peer_free(void* ptr);
 /* misc small device helpers */
 int ttb_counter_add(int* counter, int delta, void* stream);
 int ttb_transpose_f32(const float* in, int R, int Cc, float* out, void* stream);           /* [R, C] -> [C, R] */

@@ -25,6 +25,7 @@ for mode in ("single", "peer", "nccl"):
     os.environ["TTB_PEER_EXCHANGE"] = "0" if mode == "nccl" else "1"
     eng = DiffusionEngine(sd, cfg)
     pair = None if mode == "single" else (groups[0], rank)
+    print("rank", rank, "mode", mode, "starting", flush=True)
     for rep in range(3):
         dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
         mel = eng.sample(lat, cond, iters, noise0, step_noise, cond_free=True, cond_free_k=2.0, pair=pair)

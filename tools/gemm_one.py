@@ -20,6 +20,8 @@ def main():
         "clvp": (27520, 2304, 768, 1, 1, False, "bf16", 128),
         "ar": (256, 3072, 1024, 1, 1, False, "bf16", 32),
     }[which]
+    if len(sys.argv) > 3:
+        tile = int(sys.argv[3])
     dev = "cuda"
     A = torch.randn(batch, M, K, device=dev).to(torch.bfloat16)
     W = (torch.randn(N, taps * K, device=dev) * 0.02).to(torch.bfloat16)

@@ -725,8 +725,12 @@ TTB_DEVINL void attn_phase_mma(const AsParams& p, int layer, uint8_t* data, AsCt
             const int c = sub + s * p.team;
             if (c < nch) {
               mbar_arrive_expect_tx(&ctrl->ring_bar[warp][s], (uint32_t)CHUNK_BYTES);
-              tma_load_4d(ring + s * CHUNK_BYTES, map_c, &ctrl->ring_bar[warp][s], 0, 0, c * 16, item);
-              tma_load_4d(ring + s * CHUNK_BYTES + 2048, map_c, &ctrl->ring_bar[warp][s], 0, 1, c * 16, item);
+              if (p.attn_impl == 2) {
+                bulk_g2s(ring + s * CHUNK_BYTES, cb + (long long)c * 16 * 128, (uint32_t)CHUNK_BYTES, &ctrl->ring_bar[warp][s]);
+              } else {
+                tma_load_4d(ring + s * CHUNK_BYTES, map_c, &ctrl->ring_bar[warp][s], 0, 0, c * 16, item);
+                tma_load_4d(ring + s * CHUNK_BYTES + 2048, map_c, &ctrl->ring_bar[warp][s], 0, 1, c * 16, item);
+              }
             }
           }
         }
@@ -762,8 +766,12 @@ TTB_DEVINL void attn_phase_mma(const AsParams& p, int layer, uint8_t* data, AsCt
           const int c_next = c_use + NS * p.team;
           if (lane == 0 && c_next < nch) {
             mbar_arrive_expect_tx(&ctrl->ring_bar[warp][s], (uint32_t)CHUNK_BYTES);
-            tma_load_4d(ring + s * CHUNK_BYTES, map_c, &ctrl->ring_bar[warp][s], 0, 0, c_next * 16, item);
-            tma_load_4d(ring + s * CHUNK_BYTES + 2048, map_c, &ctrl->ring_bar[warp][s], 0, 1, c_next * 16, item);
+            if (p.attn_impl == 2) {
+              bulk_g2s(ring + s * CHUNK_BYTES, cb + (long long)c_next * 16 * 128, (uint32_t)CHUNK_BYTES, &ctrl->ring_bar[warp][s]);
+            } else {
+              tma_load_4d(ring + s * CHUNK_BYTES, map_c, &ctrl->ring_bar[warp][s], 0, 0, c_next * 16, item);
+              tma_load_4d(ring + s * CHUNK_BYTES + 2048, map_c, &ctrl->ring_bar[warp][s], 0, 1, c_next * 16, item);
+            }
           }
           if (++s == NS) s = 0;
         }
@@ -944,7 +952,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1) ar_step_kernel(const __grid_con
       AS_SYNC_UNLESS_LAST(1, l);
     }
     if (p.phase_mask & PH_ATTN) {
-      if (p.attn_impl == 1) attn_phase_mma(p, l, data, ctrl, rl);
+      if (p.attn_impl >= 1) attn_phase_mma(p, l, data, ctrl, rl);
       else if (p.ring_cp == 8) attn_phase<8>(p, l, data, ctrl, rl);
       else attn_phase<16>(p, l, data, ctrl, rl);
       AS_SYNC_UNLESS_LAST(2, l);
@@ -1015,7 +1023,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1) ar_attn_only_kernel(const __gri
   rl.stage = 0; rl.phase = 0; rl.acc_par = 0; rl.prefix_par = 0; rl.bar_target = 0;
   rl.ring_par[0] = rl.ring_par[1] = rl.ring_par[2] = rl.ring_par[3] = 0;
   const int l = p.layer_begin;
-  if (p.attn_impl == 1) attn_phase_mma(p, l, data, ctrl, rl);
+  if (p.attn_impl >= 1) attn_phase_mma(p, l, data, ctrl, rl);
   else if (p.ring_cp == 8) attn_phase<8>(p, l, data, ctrl, rl);
   else attn_phase<16>(p, l, data, ctrl, rl);
   pdl_launch_dependents();
@@ -1113,8 +1121,9 @@ static int make_plan(const TtbArStepArgs& a, AsPlan& pl) {
   p.team = team;
   p.prefetch = env_int("TTB_AR_STEP_PREFETCH", 1);
   p.sync_mode = env_int("TTB_AR_STEP_SYNC", 1);
-  p.attn_impl = env_int("TTB_AR_STEP_ATTN_MMA", 1) ? 1 : 0;
-  p.ring_cp = (env_int("TTB_AR_STEP_RING_CP", 16) == 8 && !p.attn_impl) ? 8 : 16;
+  p.attn_impl = env_int("TTB_AR_STEP_ATTN_MMA", 1);      // 0 SIMT, 1 tensor-core, 2 = 1 with bulk-copy fills (timing only)
+  if (p.attn_impl < 0 || p.attn_impl > 2) p.attn_impl = 1;
+  p.ring_cp = (env_int("TTB_AR_STEP_RING_CP", 16) == 8 && p.attn_impl == 0) ? 8 : 16;
   p.ring_ns = env_int("TTB_AR_STEP_RING_NS", 2);
   if (p.ring_ns < 2) p.ring_ns = 2;
   if (p.ring_ns > 4) p.ring_ns = 4;

@@ -1,6 +1,7 @@
 // CLVP helpers (rotary, pooled LayerNorm, latent projection/score), diffusion helpers (timestep embedding, small
 // fp32 linears, nearest interpolation, the fused DDPM step epilogue) and small layout utilities.
 #include "common.cuh"
+#include <cstring>
 #include "ttb_internal.h"
 
 namespace ttb {
@@ -302,6 +303,32 @@ extern "C" int ttb_pair_exchange(const float* src, float* local_area, float* pee
   TTB_CHECK_LAUNCH("pair_exchange_kernel");
   return 0;
 }
+// Exchange buffers live in their own cudaMalloc allocations (not in a caching allocator's pool) so that the IPC handle
+// describes exactly the buffer; the partner opens it with its OWN device current, which lets the driver enable peer
+// access between the two devices for that mapping (cudaIpcMemLazyEnablePeerAccess).
+extern "C" int ttb_peer_alloc(long long bytes, void** ptr, void* handle64) {
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+  if (e == cudaSuccess) e = cudaMemset(p, 0, (size_t)bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { if (p) cudaFree(p); return check_cuda(e, "ttb_peer_alloc"); }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle64, &h, 64);
+  *ptr = p;
+  return 0;
+}
+extern "C" int ttb_peer_open(const void* handle64, void** ptr) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return check_cuda(e, "cudaIpcOpenMemHandle");
+  *ptr = p;
+  return 0;
+}
+extern "C" int ttb_peer_close(void* ptr) { return check_cuda(cudaIpcCloseMemHandle(ptr), "cudaIpcCloseMemHandle"); }
+extern "C" int ttb_peer_free(void* ptr) { return check_cuda(cudaFree(ptr), "cudaFree"); }
 extern "C" int ttb_enable_peer_access(int peer_device) {
   int dev = 0;
   cudaGetDevice(&dev);

@@ -74,7 +74,7 @@ SYMBOLS = [
     "ttb_voc_lvc_gate", "ttb_voc_to_tokens_bf16", "ttb_debug_gemm_trace",
     "ttb_ar_step_workspace", "ttb_ar_step_setup", "ttb_ar_decode_step", "ttb_ar_step_store_prefix",
     "ttb_audio_resample", "ttb_audio_stft_mel", "ttb_mean_rows", "ttb_equal_linear",
-    "ttb_pair_exchange", "ttb_enable_peer_access",
+    "ttb_pair_exchange", "ttb_enable_peer_access", "ttb_peer_alloc", "ttb_peer_open", "ttb_peer_close", "ttb_peer_free",
 ]
 
 
@@ -307,6 +307,31 @@ def pair_exchange(src, local_area, peer_area, n, parity_stride, branch_off, peer
     _chk(load().ttb_pair_exchange(_p(_f32(src)), _p(_f32(local_area)), _p(_f32(peer_area)), C.c_longlong(n),
                                   C.c_longlong(parity_stride), C.c_longlong(branch_off), _p(peer_flags), _p(my_flags),
                                   _p(counter), _p(epoch), _p(done_ctr), _p(err), _stream()), "ttb_pair_exchange")
+
+
+class RawBuffer:
+    """A device buffer that is not a torch tensor (own cudaMalloc allocation or a CUDA-IPC mapping of the partner's):
+    quacks enough like a tensor for the wrappers of this module (data_ptr / dtype / is_cuda)."""
+
+    def __init__(self, ptr, dtype, numel, owned):
+        self.ptr, self.dtype, self.n, self.owned, self.is_cuda = int(ptr), dtype, int(numel), owned, True
+
+    def data_ptr(self):
+        return self.ptr
+
+
+def peer_alloc(nbytes, dtype):
+    """-> (RawBuffer, 64-byte IPC handle)."""
+    ptr = C.c_void_p(0)
+    h = C.create_string_buffer(64)
+    _chk(load().ttb_peer_alloc(C.c_longlong(nbytes), C.byref(ptr), h), "ttb_peer_alloc")
+    return RawBuffer(ptr.value, dtype, nbytes // 4, True), h.raw
+
+
+def peer_open(handle, dtype, numel):
+    ptr = C.c_void_p(0)
+    _chk(load().ttb_peer_open(C.create_string_buffer(handle, 64), C.byref(ptr)), "ttb_peer_open")
+    return RawBuffer(ptr.value, dtype, numel, False)
 
 
 def enable_peer_access(peer_device):

@@ -129,34 +129,36 @@ def exchange_utterances(parts, plan, device, dtype=torch.float32):
 
 class PairExchange:
     """Exchange area of a CFG rank pair over peer memory (CUDA IPC + NVLink stores), used by `lib.pair_exchange`
-    (csrc/misc.cu) inside the captured denoiser step. Layout of `area`: fp32 [2 step parities][2 branches][n].
-    `ok` is False when the mapping could not be set up on BOTH ranks (the caller then keeps the NCCL all-gather)."""
+    (csrc/misc.cu) inside the captured denoiser step. Layout of `area`: fp32 [2 step parities][2 branches][n]; `flags`:
+    int32, [0:2] written by the partner. Both live in their own cudaMalloc allocations (lib.peer_alloc) and are mapped into
+    the partner process with its device current. `ok` is False when the mapping could not be set up on BOTH ranks (the
+    caller then keeps the NCCL all-gather)."""
 
     def __init__(self, group, my_idx, n, device):
         import os
-        from torch.multiprocessing.reductions import reduce_tensor, rebuild_cuda_tensor
         from . import lib
         self.n, self.my_idx = int(n), int(my_idx)
-        self.area = torch.zeros(2 * 2 * self.n, dtype=torch.float32, device=device)
-        self.flags = torch.zeros(32, dtype=torch.int32, device=device)      # [0:2] written by the partner
         self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
         self.done = torch.zeros(1, dtype=torch.int32, device=device)
         self.err = torch.zeros(1, dtype=torch.int32, device=device)
-        self.peer_area = self.peer_flags = None
-        ok = os.environ.get("TTB_PEER_EXCHANGE", "1") == "1" and self.area.is_cuda
+        self.area = self.flags = self.peer_area = self.peer_flags = None
+        ok = os.environ.get("TTB_PEER_EXCHANGE", "1") == "1" and torch.device(device).type == "cuda"
+        mine = None
+        if ok:
+            try:
+                self.area, ha = lib.peer_alloc(4 * 2 * 2 * self.n, torch.float32)
+                self.flags, hf = lib.peer_alloc(4 * 32, torch.int32)
+                mine = (ha, hf)
+            except lib.TtbError:
+                ok = False
         metas = [None, None]
-        try:
-            mine = (reduce_tensor(self.area)[1], reduce_tensor(self.flags)[1]) if ok else None
-        except Exception:           # noqa: BLE001  (e.g. an allocator mode without IPC support)
-            mine, ok = None, False
         dist.all_gather_object(metas, mine, group=group)
         peer = metas[1 - self.my_idx]
         if ok and peer is not None:
             try:
-                self.peer_area = rebuild_cuda_tensor(*peer[0])
-                self.peer_flags = rebuild_cuda_tensor(*peer[1])
-                lib.enable_peer_access(self.peer_area.device.index)
-            except Exception:       # noqa: BLE001
+                self.peer_area = lib.peer_open(peer[0], torch.float32, 2 * 2 * self.n)
+                self.peer_flags = lib.peer_open(peer[1], torch.int32, 32)
+            except lib.TtbError:
                 ok = False
         else:
             ok = False
