@@ -51,6 +51,11 @@ typedef struct TtbGemmArgs {
                            per CTA with a 5- / 4-stage pipeline (tools/gemm_sweep.py, tools/gemm_diag.py).
                            Experiments not yet validated on hardware (never chosen automatically): 5 = two TMA issuer
                            threads per CTA, 6 = CTA-pair kernel (tcgen05 cta_group::2, 256 x tile_n tiles, tile_n 128 / 256) */
+  float* gn_partials;   /* non-NULL: the epilogue also leaves the GroupNorm statistics of its OUTPUT (after bias, activation
+                           and residual) in a ttb_groupnorm scratch buffer: (sum, sum of squares) of every 32-row x 32-column
+                           block, i.e. one partial per (batch item, group, row block) for 32 channels per group. Needs
+                           N == 32 * gn_groups and ceil(M / 32) <= TTB_GROUPNORM_SPLITS; consumed by ttb_groupnorm_apply. */
+  int gn_groups;
 } TtbGemmArgs;
 
 /* nn.Linear / HF Conv1D / nn.Conv1d(k=1,3) as one tcgen05 GEMM with fused bias/activation/residual.
@@ -90,6 +95,11 @@ int ttb_rmsnorm(const float* x, int M, int D, const float* g, void* out_bf16, vo
 int ttb_groupnorm(const float* x, int B, int S, int C, int groups, const float* gamma, const float* beta,
                   const float* scale_shift, int ss_bstride, const int* ss_row, int ss_row_stride, int silu,
                   float* partials, void* out_bf16, int ldo, float* out_f32, int ldof, void* stream);
+/* The apply half of ttb_groupnorm alone, for an x whose statistics the producing ttb_gemm already left in `partials`
+ * (TtbGemmArgs.gn_partials, one partial per 32-row block): x is read once instead of twice. 32 channels per group. */
+int ttb_groupnorm_apply(const float* x, int B, int S, int C, int groups, const float* gamma, const float* beta,
+                        const float* scale_shift, int ss_bstride, const int* ss_row, int ss_row_stride, int silu,
+                        const float* partials, void* out_bf16, int ldo, float* out_f32, int ldof, void* stream);
 
 /* ---------------------------------------------------------------- attention */
 typedef struct TtbAttnArgs {

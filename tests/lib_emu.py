@@ -16,7 +16,7 @@ def _v(t, sizes, strides):
 
 def gemm(A, W, *, M, N, K, bias=None, residual=None, out_f32=None, out_bf16=None, lda=None, rows=None, batch=1,
          a_bstride=0, res_bstride=0, outf_bstride=0, outb_bstride=0, ldr=None, ldo=None, ldob=None, taps=1, pad=0,
-         act=ACT_NONE, alpha=1.0, tile_n=0, force_ref=False, splitk=1, cluster=0, variant=0):
+         act=ACT_NONE, alpha=1.0, tile_n=0, force_ref=False, splitk=1, cluster=0, variant=0, gn_partials=None, gn_groups=0):
     n_out = N // 2 if act == ACT_GEGLU else N
     lda = K if lda is None else lda
     rows = M if rows is None else rows
@@ -56,6 +56,15 @@ def gemm(A, W, *, M, N, K, bias=None, residual=None, out_f32=None, out_bf16=None
         _v(out_f32, (batch, M, n_out), (outf_bstride, ldo, 1)).copy_(acc)
     if out_bf16 is not None:
         _v(out_bf16, (batch, M, n_out), (outb_bstride, ldob, 1)).copy_(acc.to(torch.bfloat16))
+    if gn_partials is not None:
+        # (sum, sum of squares) per (batch item, group of 32 columns, block of 32 rows), scratch layout of csrc/norm.cu
+        assert N == 32 * gn_groups and (M + 31) // 32 <= 128 and act != ACT_GEGLU and splitk <= 1
+        nrb = (M + 31) // 32
+        pad_rows = nrb * 32 - M
+        blk = F.pad(acc, (0, 0, 0, pad_rows)).reshape(batch, nrb, 32, gn_groups, 32)
+        part = _v(gn_partials[16:], (batch, gn_groups, 128, 2), (gn_groups * 256, 256, 2, 1))
+        part[:, :, :nrb, 0] = blk.sum(dim=(2, 4)).transpose(1, 2)
+        part[:, :, :nrb, 1] = (blk * blk).sum(dim=(2, 4)).transpose(1, 2)
 
 
 def layernorm(x, M, D, g1, b1, g2=None, b2=None, out_bf16=None, out_f32=None):
@@ -98,6 +107,30 @@ def groupnorm(x, B, S, Cc, groups, gamma, beta, partials, scale_shift=None, ss_b
     if silu:
         y = F.silu(y)
     y = y.transpose(1, 2)
+    if out_bf16 is not None:
+        _v(out_bf16, (B, S, Cc), (S * ldo, ldo, 1)).copy_(y.to(torch.bfloat16))
+    if out_f32 is not None:
+        _v(out_f32, (B, S, Cc), (S * ldof, ldof, 1)).copy_(y)
+
+
+def groupnorm_apply(x, B, S, Cc, groups, gamma, beta, partials, scale_shift=None, ss_bstride=0, ss_row=None,
+                    ss_row_stride=0, silu=False, out_bf16=None, ldo=0, out_f32=None, ldof=0):
+    """Uses the statistics the producing gemm(..., gn_partials=) left behind (NOT recomputed from x: a stale-partials
+    bug in the host logic must show up as a mismatch)."""
+    assert Cc == 32 * groups
+    nrb = (S + 31) // 32
+    part = _v(partials[16:], (B, groups, 128, 2), (groups * 256, 256, 2, 1))[:, :, :nrb].sum(dim=2)
+    n = float(S * 32)
+    mean = part[..., 0] / n
+    rstd = torch.rsqrt((part[..., 1] / n - mean * mean).clamp(min=0) + 1e-5)
+    xx = _v(x, (B, S, groups, 32), (S * Cc, Cc, 32, 1))
+    y = ((xx - mean[:, None, :, None]) * rstd[:, None, :, None]).reshape(B, S, Cc) * gamma + beta
+    if scale_shift is not None:
+        off = int(ss_row[0]) * ss_row_stride if ss_row is not None else 0
+        ss = torch.as_strided(scale_shift, (B, 2 * Cc), (ss_bstride, 1), scale_shift.storage_offset() + off)
+        y = y * (1 + ss[:, None, :Cc]) + ss[:, None, Cc:]
+    if silu:
+        y = F.silu(y)
     if out_bf16 is not None:
         _v(out_bf16, (B, S, Cc), (S * ldo, ldo, 1)).copy_(y.to(torch.bfloat16))
     if out_f32 is not None:

@@ -70,6 +70,37 @@ def test_groupnorm_fused(C, groups, S):
         assert (of - want).abs().max().item() < 1e-3
 
 
+@pytest.mark.parametrize("S,taps,residual,kw", [(1872, 3, True, {}), (1872, 1, False, {}), (43, 1, True, {}),
+                                                 (500, 3, True, dict(variant=2)), (256, 1, False, dict(tile_n=64)),
+                                                 (1000, 1, True, dict(cluster=2)), (2176, 3, True, {})])
+def test_gemm_groupnorm_statistics_in_epilogue(S, taps, residual, kw):
+    """TtbGemmArgs.gn_partials: the GEMM epilogue leaves (sum, sum of squares) per 32 x 32 output block and
+    ttb_groupnorm_apply normalises from them; against F.group_norm of the GEMM's own fp32 output (GroupNorm32,
+    arch_util.py:21-41) and against the two-pass ttb_groupnorm."""
+    from tortoise_tts_b200 import lib
+    torch.manual_seed(11)
+    B, C, groups = 2, 1024, 32
+    a = (torch.randn(B, S, C, device="cuda") * 0.5).to(torch.bfloat16)
+    w = (torch.randn(C, taps * C, device="cuda") * 0.03).to(torch.bfloat16)
+    bias = torch.randn(C, device="cuda")
+    x = torch.randn(B, S, C, device="cuda") + 0.3
+    part = lib.groupnorm_scratch(B, groups, "cuda")
+    part.fill_(float("nan"))                       # every partial that is read must have been written by the GEMM
+    out = x.clone() if residual else torch.empty_like(x)
+    lib.gemm(a, w, M=S, N=C, K=C, taps=taps, pad=taps // 2, bias=bias, residual=out if residual else None, out_f32=out,
+             batch=B, a_bstride=S * C, res_bstride=S * C, outf_bstride=S * C, gn_partials=part, gn_groups=groups, **kw)
+    gamma, beta = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
+    got = torch.empty(B, S, C, device="cuda")
+    lib.groupnorm_apply(out, B, S, C, groups, gamma, beta, part, silu=True, out_f32=got, ldof=C)
+    want = F.silu(F.group_norm(out.transpose(1, 2), groups, gamma, beta, 1e-5)).transpose(1, 2)
+    err = (got - want).abs().max().item()
+    report("gemm-epilogue groupnorm statistics S=%d taps=%d %s" % (S, taps, kw), err)
+    assert err < 1e-3
+    two = torch.empty(B, S, C, device="cuda")
+    lib.groupnorm(out, B, S, C, groups, gamma, beta, lib.groupnorm_scratch(B, groups, "cuda"), silu=True, out_f32=two, ldof=C)
+    assert (got - two).abs().max().item() < 1e-3
+
+
 @pytest.mark.parametrize("T,H,nseq,causal,use_bias", [(45, 2, 2, False, True), (174, 16, 1, True, False),
                                                       (374, 16, 2, False, True), (130, 12, 3, False, False),
                                                       (64, 2, 1, False, False), (128, 2, 2, True, True),

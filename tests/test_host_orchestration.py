@@ -78,6 +78,38 @@ def test_diffusion_engine(env):
     assert err < 1.5 and rms < 0.3, (err, rms)
 
 
+def test_diffusion_engine_fused_groupnorm_statistics(env):
+    """Full-width denoiser (C = 1024: 32 channels per group, the case where the GEMM epilogue leaves the GroupNorm
+    statistics for the GroupNorm that follows): one cond + uncond evaluation against the oracle with the fused statistics
+    on and off. The emulated groupnorm_apply uses ONLY the partials the emulated gemm stored, so a block that consumes
+    stale partials fails here."""
+    from tortoise_tts_b200.diffusion_engine import DiffusionEngine
+    from tortoise_tts_b200.synth import synth_diffusion
+    from oracle import diffusion as od
+    cfg = ModelConfig.medium()
+    sd = synth_diffusion(cfg, 0)
+    torch.manual_seed(7)
+    N, S = 10, 43                                      # S % 32 != 0: ragged last row block
+    lat = torch.randn(N, cfg.ar_dim)
+    cond = torch.randn(2 * cfg.diff_dim) * 0.3
+    x = torch.randn(1, 100, S)
+    with torch.no_grad():
+        ce = od.timestep_independent(sd, cfg, lat.unsqueeze(0), cond.unsqueeze(0), S)
+        want_c = od.forward(sd, cfg, x, torch.tensor([1000]), code_emb=ce)
+        want_u = od.forward(sd, cfg, x, torch.tensor([1000]), conditioning_free=True)
+    outs = {}
+    for fused in (1, 0):
+        eng = DiffusionEngine(sd, cfg, device="cpu")
+        eng.GN_FUSED = fused
+        ce_g = eng.timestep_independent(lat, cond, S)
+        assert _rel(ce_g.t(), ce[0]) < 0.03
+        got_c, got_u = eng.forward_once(x[0], 1000, ce_g)
+        assert _rel(got_c, want_c[0]) < 0.03 and _rel(got_u, want_u[0]) < 0.03, fused
+        outs[fused] = (got_c, got_u)
+    # (fp32 statistics summed in a different order flip a few bf16 roundings of the normalised operand: ~0.3 %)
+    assert _rel(outs[1][0], outs[0][0]) < 0.01 and _rel(outs[1][1], outs[0][1]) < 0.01
+
+
 def test_vocoder_engine(env):
     from tortoise_tts_b200.vocoder_engine import VocoderEngine
     cfg, sds, g = env

@@ -18,7 +18,7 @@ import torch  # noqa: E402
 
 def instrument(lib, records):
     names = [n for n in dir(lib) if callable(getattr(lib, n)) and n in (
-        "gemm", "layernorm", "residual_layernorm", "rmsnorm", "groupnorm", "attention", "ar_embed_step",
+        "gemm", "layernorm", "residual_layernorm", "rmsnorm", "groupnorm", "groupnorm_apply", "attention", "ar_embed_step",
         "ar_decode_attention", "ar_sample", "diffusion_step", "cast_pad_bf16", "counter_add", "clvp_rotary")]
     saved = {}
     for n in names:

@@ -46,10 +46,12 @@ def build(force=False, verbose=False):
         ok = ok and p.returncode == 0
     if not ok:
         raise RuntimeError("nvcc failed")
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [nvcc, "-shared", "-o", LIB + ".tmp"] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
-    with open(STAMP, "w") as f:
+    os.replace(LIB + ".tmp", LIB)          # atomic: a concurrent reader (repo snapshot) sees the old or the new library
+    with open(STAMP + ".tmp", "w") as f:
         f.write(want + "\n")
+    os.replace(STAMP + ".tmp", STAMP)
     return LIB
 
 

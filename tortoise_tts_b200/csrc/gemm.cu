@@ -118,6 +118,8 @@ struct GemmEpilogue {
   int ldr, ldo, ldob;
   int act;                 // TTB_ACT_*
   float alpha;             // scales the accumulator before bias
+  float2* gn_part;         // GroupNorm partials [batch][groups][TTB_GN_SPLITS] of the output, or null (TtbGemmArgs.gn_partials)
+  int gn_groups;
 };
 
 }  // namespace ttb
@@ -417,6 +419,15 @@ extern "C" int ttb_gemm(const TtbGemmArgs* gp, void* stream) {
   ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(g.out_bf16);
   ep.res_bstride = g.res_bstride; ep.outf_bstride = g.outf_bstride; ep.outb_bstride = g.outb_bstride;
   ep.ldr = g.ldr; ep.ldo = g.ldo; ep.ldob = g.ldob; ep.act = g.act; ep.alpha = g.alpha;
+  ep.gn_part = nullptr; ep.gn_groups = g.gn_groups;
+  if (g.gn_partials) {
+    if (g.N != 32 * g.gn_groups || (g.M + 31) / 32 > TTB_GN_SPLITS || g.act == TTB_ACT_GEGLU || g.splitk > 1 || g.force_ref) {
+      set_error("ttb_gemm: gn_partials needs N == 32 * gn_groups, M <= %d, no GEGLU / split-K (N=%d groups=%d M=%d)",
+                32 * TTB_GN_SPLITS, g.N, g.gn_groups, g.M);
+      return -1;
+    }
+    ep.gn_part = reinterpret_cast<float2*>(g.gn_partials + 16);   // scratch layout of norm.cu: 16 floats, then the partials
+  }
   if (g_gemm_impl < 0) {
     const char* e = getenv("TTB_GEMM_IMPL");
     g_gemm_impl = (e && strcmp(e, "ref") == 0) ? 1 : 0;

@@ -64,6 +64,18 @@ TTB_DEVINL EpiFlags epi_flags(const GemmEpilogue& ep) {
   return f;
 }
 
+// (sum, sum of squares) of one 32-row x 32-column block of the output = one GroupNorm partial (32 channels per group):
+// fixed xor tree, one writer, no atomics (bit-reproducible).
+TTB_DEVINL void epi_gn_store(float gs, float gq, int nb, int m_base, int lane, long long bz, const GemmEpilogue& ep) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    gs += __shfl_xor_sync(0xffffffffu, gs, off);
+    gq += __shfl_xor_sync(0xffffffffu, gq, off);
+  }
+  if (lane == 0)
+    ep.gn_part[((long long)bz * ep.gn_groups + (nb >> 5)) * TTB_GN_SPLITS + (m_base >> 5)] = make_float2(gs, gq);
+}
+
 // ---- FAST path: all 32 rows and 32 columns exist, everything aligned. Branch-free apart from the uniform pointer tests.
 template <int ACT>
 TTB_DEVINL void epi_chunk_fast(const uint32_t* r, int nb, int m_base, int lane, long long bz, const GemmEpilogue& ep,
@@ -118,6 +130,7 @@ TTB_DEVINL void epi_chunk_fast(const uint32_t* r, int nb, int m_base, int lane, 
     sts128(wrow + k * 16, epi_act<ACT>(v[4 * k]), epi_act<ACT>(v[4 * k + 1]), epi_act<ACT>(v[4 * k + 2]),
            epi_act<ACT>(v[4 * k + 3]));
   __syncwarp();
+  float gs = 0.f, gq = 0.f;                          // GroupNorm partial of this 32 x 32 block (ep.gn_part)
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int rr = it * 4 + rr0;
@@ -127,13 +140,17 @@ TTB_DEVINL void epi_chunk_fast(const uint32_t* r, int nb, int m_base, int lane, 
     if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + bz * ep.outf_bstride + m * ep.ldo + col) = o;
     if (ep.out_bf16)
       *reinterpret_cast<uint2*>(ep.out_bf16 + bz * ep.outb_bstride + m * ep.ldob + col) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+    gs += (o.x + o.y) + (o.z + o.w);
+    gq += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
   }
+  if (ep.gn_part) epi_gn_store(gs, gq, nb, m_base, lane, bz, ep);
   __syncwarp();                                      // scratch is reused by the next chunk
 }
 
 // ---- SLOW path (ragged M / N edges, unaligned rows): each lane finishes its own accumulator row with scalar accesses.
 template <int ACT>
-TTB_DEVINL void epi_chunk_slow(const uint32_t* r, int nb, int N, int m, int M, long long bz, const GemmEpilogue& ep) {
+TTB_DEVINL void epi_chunk_slow(const uint32_t* r, int nb, int N, int m, int M, long long bz, const GemmEpilogue& ep,
+                               float& gs, float& gq) {
   if (m >= M) return;
   if (ACT == TTB_ACT_GEGLU) {
     const int nout = N >> 1, ob = nb >> 1;
@@ -163,6 +180,8 @@ TTB_DEVINL void epi_chunk_slow(const uint32_t* r, int nb, int N, int m, int M, l
       if (rp) x += rp[nb + j];
       if (of) of[nb + j] = x;
       if (obf) obf[nb + j] = __float2bfloat16(x);
+      gs += x;
+      gq += x * x;
     }
   }
 }
@@ -186,7 +205,11 @@ TTB_DEVINL void gemm_epilogue_tile(uint32_t taddr, int n0, int N, int m_base, in
     if (release_bar && ch == NCH - 1) { tc_fence_before(); mbar_arrive(release_bar); }
     if (nb >= N) continue;                           // warp-uniform
     if (rows_full && nb + 32 <= N) epi_chunk_fast<ACT>(r, nb, m_base, lane, bz, ep, scratch);
-    else epi_chunk_slow<ACT>(r, nb, N, m_base + lane, M, bz, ep);
+    else {
+      float gs = 0.f, gq = 0.f;                      // rows past M contribute nothing
+      epi_chunk_slow<ACT>(r, nb, N, m_base + lane, M, bz, ep, gs, gq);
+      if (ep.gn_part && m_base < M) epi_gn_store(gs, gq, nb, m_base, lane, bz, ep);
+    }
   }
 }
 

@@ -428,6 +428,25 @@ extern "C" int ttb_rmsnorm(const float* x, int M, int D, const float* g, void* o
   return 0;
 }
 
+extern "C" int ttb_groupnorm_apply(const float* x, int B, int S, int C, int groups, const float* gamma, const float* beta,
+                                   const float* scale_shift, int ss_bstride, const int* ss_row, int ss_row_stride,
+                                   int do_silu, const float* partials, void* out_bf16, int ldo, float* out_f32, int ldof,
+                                   void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int splits = (S + 31) / 32;                 // one partial per 32-row block, written by the GEMM epilogue
+  if (C != 32 * groups || C > 1024 || (C & (C - 1)) || splits > TTB_GN_SPLITS || S <= 0) {
+    set_error("ttb_groupnorm_apply: needs 32 channels per group, C a power of two <= 1024, S <= %d (C=%d groups=%d S=%d)",
+              32 * TTB_GN_SPLITS, C, groups, S);
+    return -1;
+  }
+  const int tpr = C >> 2, rows_par = 256 / tpr, rows_per_a = 16 * rows_par;
+  launch_pdl(gn_apply_rows_kernel, dim3((S + rows_per_a - 1) / rows_per_a, B), dim3(256), (size_t)0, st,
+      x, S, C, groups, 32, tpr, rows_per_a, splits, partials, gamma, beta, scale_shift, ss_bstride, ss_row, ss_row_stride,
+      do_silu, reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo, out_f32, ldof);
+  TTB_CHECK_LAUNCH("gn_apply_rows_kernel");
+  return 0;
+}
+
 extern "C" int ttb_groupnorm(const float* x, int B, int S, int C, int groups, const float* gamma, const float* beta,
                              const float* scale_shift, int ss_bstride, const int* ss_row, int ss_row_stride,
                              int do_silu, float* partials, void* out_bf16, int ldo, float* out_f32, int ldof,

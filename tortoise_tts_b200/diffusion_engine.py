@@ -162,31 +162,49 @@ class DiffusionEngine:
         import os
         cl = int(os.environ.get("TTB_DIFF_CLUSTER", "0"))
         self.CL = cl if (cl in (2, 4) and (C // 128) % cl == 0) else 0
+        # GroupNorm statistics taken in the epilogue of the producing GEMM (TTB_GN_FUSED=0: separate statistics pass)
+        self.GN_FUSED = int(os.environ.get("TTB_GN_FUSED", "1"))
 
     # ------------------------------------------------------------------ building blocks on [B, S, C] fp32 (in place)
-    def _gn(self, x, B, S, g, b, ws, silu=False, ss=None, ss_row=None, out=None):
-        lib.groupnorm(x, B, S, self.C, self.groups, g, b, ws["partials"], scale_shift=ss, ss_bstride=0, ss_row=ss_row,
-                      ss_row_stride=2 * self.C, silu=silu, out_bf16=ws["a"] if out is None else out, ldo=self.C)
+    def _gn(self, x, B, S, g, b, ws, silu=False, ss=None, ss_row=None, out=None, ready=False):
+        """GroupNorm32 (+scale/shift, +SiLU) of x into the bf16 GEMM operand. `ready`: the GEMM that produced x already
+        left the statistics in ws['partials'] (see _gnp), so x is read once."""
+        fn = lib.groupnorm_apply if ready else lib.groupnorm
+        fn(x, B, S, self.C, self.groups, g, b, ws["partials"], scale_shift=ss, ss_bstride=0, ss_row=ss_row,
+           ss_row_stride=2 * self.C, silu=silu, out_bf16=ws["a"] if out is None else out, ldo=self.C)
 
-    def _attn_block(self, aw, x, B, S, ws):
+    def _gnp(self, S, ws):
+        """kwargs that make a C-wide GEMM leave the GroupNorm statistics of its output for the GroupNorm that follows
+        (TtbGemmArgs.gn_partials): 32 channels per group and at most TTB_GROUPNORM_SPLITS row blocks of 32."""
+        if self.GN_FUSED and self.C == 32 * self.groups and (S + 31) // 32 <= 128:
+            return dict(gn_partials=ws["partials"], gn_groups=self.groups)
+        return {}
+
+    def _attn_block(self, aw, x, B, S, ws, ready=False):
+        """AttentionBlock (arch_util.py:80-123). Returns whether x's GroupNorm statistics are ready for the next block."""
         C, H = self.C, self.H
-        self._gn(x, B, S, aw.gn_g, aw.gn_b, ws)
+        gp = self._gnp(S, ws)
+        self._gn(x, B, S, aw.gn_g, aw.gn_b, ws, ready=ready)
         lib.gemm(ws["a"], aw.wqkv, M=S, N=3 * C, K=C, bias=aw.bqkv, out_bf16=ws["qkv"], batch=B, a_bstride=S * C,
                  outb_bstride=S * 3 * C, cluster=self.CL)
         # T5 buckets saturate at max_distance = 64 (xtransformers.py:166-174): |j - i| >= 64 -> constant bias per side
         lib.attention(ws["qkv"], ws["o"], nseq=B, T=S, H=H, ld=3 * C, ldo=C, k_off=C, v_off=2 * C, scale=0.125,
                       bias=aw.table(S), bias_sat=64)
         lib.gemm(ws["o"], aw.wproj, M=S, N=C, K=C, bias=aw.bproj, residual=x, out_f32=x, batch=B, a_bstride=S * C,
-                 res_bstride=S * C, outf_bstride=S * C, cluster=self.CL)
+                 res_bstride=S * C, outf_bstride=S * C, cluster=self.CL, **gp)
+        return bool(gp)
 
-    def _res_block(self, rw, ss, x, B, S, ws, ss_row=None):
+    def _res_block(self, rw, ss, x, B, S, ws, ss_row=None, ready=False):
+        """ResBlock (diffusion_decoder.py:60-120); `ready` / return value as in _attn_block."""
         C = self.C
-        self._gn(x, B, S, rw.in_g, rw.in_b, ws, silu=True)
+        gp = self._gnp(S, ws)
+        self._gn(x, B, S, rw.in_g, rw.in_b, ws, silu=True, ready=ready)
         lib.gemm(ws["a"], rw.w_in, M=S, N=C, K=C, bias=rw.b_in, out_f32=ws["h"], batch=B, a_bstride=S * C,
-                 outf_bstride=S * C, cluster=self.CL)
-        self._gn(ws["h"], B, S, rw.out_g, rw.out_b, ws, silu=True, ss=ss, ss_row=ss_row)
+                 outf_bstride=S * C, cluster=self.CL, **gp)
+        self._gn(ws["h"], B, S, rw.out_g, rw.out_b, ws, silu=True, ss=ss, ss_row=ss_row, ready=bool(gp))
         lib.gemm(ws["a"], rw.w_out, M=S, N=C, K=C, taps=3, pad=1, bias=rw.b_out, residual=x, out_f32=x, batch=B,
-                 a_bstride=S * C, res_bstride=S * C, outf_bstride=S * C, cluster=self.CL)
+                 a_bstride=S * C, res_bstride=S * C, outf_bstride=S * C, cluster=self.CL, **gp)
+        return bool(gp)
 
     def _alloc(self, B, S):
         C, dev = self.C, self.dev
@@ -224,24 +242,27 @@ class DiffusionEngine:
         C, B, S, ws = self.C, st["B"], st["S"], st["ws"]
         xce = st["xce"]
         xce.copy_(st["code_emb_init"])
+        rdy = False          # are the GroupNorm statistics of the running activation already in ws["partials"]?
         for j, (rw, aw) in enumerate(self.integ):
-            self._res_block(rw, st["ss_all"][j], xce, B, S, ws, st["counter"])
-            self._attn_block(aw, xce, B, S, ws)
+            rdy = self._res_block(rw, st["ss_all"][j], xce, B, S, ws, st["counter"], ready=rdy)
+            rdy = self._attn_block(aw, xce, B, S, ws, ready=rdy)
         cat = st["cat"]
         # inp_block conv on the shared sample x (a_bstride 0 broadcasts it to both branches); writes cat[..., :C]
         lib.gemm(st["x_bf"], self.w_inp, M=S, N=C, K=self.cin_pad, taps=3, pad=1, bias=self.b_inp, out_bf16=cat, ldob=2 * C,
                  batch=B, a_bstride=0, outb_bstride=S * 2 * C)
         lib.cast_pad_bf16(xce, B * S, C, C, cat[:, :, C:], 2 * C, ncols_out=C)
         x = st["xm"]
+        gp = self._gnp(S, ws)
         lib.gemm(cat, self.w_integ, M=S, N=C, K=2 * C, bias=self.b_integ, out_f32=x, batch=B, a_bstride=S * 2 * C,
-                 outf_bstride=S * C)
+                 outf_bstride=S * C, **gp)
+        rdy = bool(gp)
         n_int = len(self.integ)
         for j, (rw, aw) in enumerate(self.layers):
-            self._res_block(rw, st["ss_all"][n_int + j], x, B, S, ws, st["counter"])
-            self._attn_block(aw, x, B, S, ws)
+            rdy = self._res_block(rw, st["ss_all"][n_int + j], x, B, S, ws, st["counter"], ready=rdy)
+            rdy = self._attn_block(aw, x, B, S, ws, ready=rdy)
         for j, rw in enumerate(self.tail):
-            self._res_block(rw, st["ss_all"][n_int + len(self.layers) + j], x, B, S, ws, st["counter"])
-        self._gn(x, B, S, self.out_g, self.out_b, ws, silu=True)
+            rdy = self._res_block(rw, st["ss_all"][n_int + len(self.layers) + j], x, B, S, ws, st["counter"], ready=rdy)
+        self._gn(x, B, S, self.out_g, self.out_b, ws, silu=True, ready=rdy)
         lib.gemm(ws["a"], self.w_outc, M=S, N=self.cout, K=C, taps=3, pad=1, bias=self.b_outc, out_f32=st["mo_local"],
                  batch=B, a_bstride=S * C, outf_bstride=S * self.cout)
 

@@ -25,7 +25,8 @@ class GemmArgs(C.Structure):
                 ("lda", C.c_int), ("ldr", C.c_int), ("ldo", C.c_int), ("ldob", C.c_int),
                 ("rows", C.c_int), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
                 ("taps", C.c_int), ("pad", C.c_int), ("batch", C.c_int), ("act", C.c_int),
-                ("alpha", C.c_float), ("tile_n", C.c_int), ("force_ref", C.c_int), ("splitk", C.c_int), ("cluster", C.c_int), ("variant", C.c_int)]
+                ("alpha", C.c_float), ("tile_n", C.c_int), ("force_ref", C.c_int), ("splitk", C.c_int), ("cluster", C.c_int), ("variant", C.c_int),
+                ("gn_partials", C.c_void_p), ("gn_groups", C.c_int)]
 
 
 class AttnArgs(C.Structure):
@@ -66,7 +67,7 @@ _lib = None
 
 # every symbol include/ttb.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
-    "ttb_last_error", "ttb_version", "ttb_device_ok", "ttb_gemm", "ttb_layernorm", "ttb_rmsnorm", "ttb_groupnorm",
+    "ttb_last_error", "ttb_version", "ttb_device_ok", "ttb_gemm", "ttb_layernorm", "ttb_rmsnorm", "ttb_groupnorm", "ttb_groupnorm_apply",
     "ttb_residual_layernorm", "ttb_attention", "ttb_ar_embed_step", "ttb_ar_decode_attention", "ttb_ar_store_prefix", "ttb_ar_sample",
     "ttb_ar_fix_codes", "ttb_embed", "ttb_clvp_rotary", "ttb_clvp_pool", "ttb_clvp_project",
     "ttb_timestep_embedding", "ttb_linear_small", "ttb_interp_nearest", "ttb_diffusion_step", "ttb_counter_add",
@@ -130,8 +131,9 @@ def _f32(t):
 # ------------------------------------------------------------------ wrappers
 def gemm(A, W, *, M, N, K, bias=None, residual=None, out_f32=None, out_bf16=None, lda=None, rows=None, batch=1,
          a_bstride=0, res_bstride=0, outf_bstride=0, outb_bstride=0, ldr=None, ldo=None, ldob=None, taps=1, pad=0,
-         act=ACT_NONE, alpha=1.0, tile_n=0, force_ref=False, splitk=1, cluster=0, variant=0):
-    """See include/ttb.h ttb_gemm. A: bf16 [batch, rows, lda]; W: bf16 [N, taps*K]."""
+         act=ACT_NONE, alpha=1.0, tile_n=0, force_ref=False, splitk=1, cluster=0, variant=0, gn_partials=None, gn_groups=0):
+    """See include/ttb.h ttb_gemm. A: bf16 [batch, rows, lda]; W: bf16 [N, taps*K]. `gn_partials` (a groupnorm_scratch
+    buffer): the epilogue also leaves the GroupNorm statistics of the output there (consumed by groupnorm_apply)."""
     _bf(A), _bf(W), _f32(bias), _f32(residual), _f32(out_f32), _bf(out_bf16)
     n_out = N // 2 if act == ACT_GEGLU else N
     g = GemmArgs()
@@ -146,6 +148,7 @@ def gemm(A, W, *, M, N, K, bias=None, residual=None, out_f32=None, out_bf16=None
     g.M, g.N, g.K, g.taps, g.pad, g.batch, g.act = M, N, K, taps, pad, batch, act
     g.alpha, g.tile_n, g.force_ref, g.splitk, g.cluster = alpha, tile_n, 1 if force_ref else 0, splitk, cluster
     g.variant = variant
+    g.gn_partials, g.gn_groups = _p(_f32(gn_partials)).value or 0, gn_groups
     _chk(load().ttb_gemm(C.byref(g), _stream()), "ttb_gemm")
 
 
@@ -180,6 +183,14 @@ def groupnorm(x, B, S, Cc, groups, gamma, beta, partials, scale_shift=None, ss_b
     _chk(load().ttb_groupnorm(_p(_f32(x)), B, S, Cc, groups, _p(gamma), _p(beta), _p(scale_shift), ss_bstride,
                               _p(ss_row), ss_row_stride, 1 if silu else 0, _p(partials), _p(_bf(out_bf16)), ldo, _p(_f32(out_f32)), ldof,
                               _stream()), "ttb_groupnorm")
+
+
+def groupnorm_apply(x, B, S, Cc, groups, gamma, beta, partials, scale_shift=None, ss_bstride=0, ss_row=None,
+                    ss_row_stride=0, silu=False, out_bf16=None, ldo=0, out_f32=None, ldof=0):
+    """The apply half of groupnorm for an x whose statistics a gemm(..., gn_partials=partials) already produced."""
+    _chk(load().ttb_groupnorm_apply(_p(_f32(x)), B, S, Cc, groups, _p(gamma), _p(beta), _p(scale_shift), ss_bstride,
+                                    _p(ss_row), ss_row_stride, 1 if silu else 0, _p(partials), _p(_bf(out_bf16)), ldo,
+                                    _p(_f32(out_f32)), ldof, _stream()), "ttb_groupnorm_apply")
 
 
 def attention(qkv, out, *, nseq, T, H, ld, ldo, k_off, v_off, scale, causal=False, bias=None, bias_sat=0, head_dim=0):
