@@ -41,7 +41,14 @@ def main():
         ("ar fc", 256, 4096, 1024, 1, 1, False, "bf16"),
         ("ar proj2", 256, 1024, 4096, 1, 1, False, "f32"),
     ]
+    only = os.environ.get("TTB_SWEEP_SHAPES")            # e.g. "diff": shapes whose name contains the string
+    quick = os.environ.get("TTB_SWEEP_QUICK") == "1"      # tile 64 / 128 variants only; adds M = 1920 (no ragged edge)
+    if quick:
+        shapes += [("diff conv k3 M=1920", 1920, 1024, 1024, 3, 2, True, "f32"),
+                   ("diff conv1x1 M=1920", 1920, 1024, 1024, 1, 2, True, "f32")]
     for name, M, N, K, taps, batch, res, out in shapes:
+        if only and only not in name:
+            continue
         A = torch.randn(batch, M, K, device=dev).to(torch.bfloat16)
         W = (torch.randn(N, taps * K, device=dev) * 0.02).to(torch.bfloat16)
         bias = torch.zeros(N, device=dev)
@@ -55,7 +62,7 @@ def main():
         print("== %-13s M=%dx%d N=%d K=%d taps=%d  (%.1f GFLOP)   cuBLAS bf16: %7.1f us  %6.0f TF/s" %
               (name, batch, M, N, K, taps, flops / 1e9, t_cublas, flops / t_cublas / 1e6))
         variants = []
-        for tile in (32, 64, 128, 256):
+        for tile in ((64, 128) if quick else (32, 64, 128, 256)):
             if M <= 256 and tile == 256:
                 continue
             for variant in (1, 2):

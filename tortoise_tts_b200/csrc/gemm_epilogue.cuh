@@ -76,11 +76,15 @@ TTB_DEVINL void epi_gn_store(float gs, float gq, int nb, int m_base, int lane, l
     ep.gn_part[((long long)bz * ep.gn_groups + (nb >> 5)) * TTB_GN_SPLITS + (m_base >> 5)] = make_float2(gs, gq);
 }
 
-// ---- FAST path: all 32 rows and 32 columns exist, everything aligned. Branch-free apart from the uniform pointer tests.
+// ---- FAST path: all 32 columns exist, everything aligned. Branch-free apart from the uniform pointer tests. Only the
+// first `rows_valid` (1..32) of the 32 rows exist (< 32: the last row block of a ragged M): the row-wise residual loads
+// and stores are predicated per row -- one code path, so the kernels' register allocation and code size stay as they were. (The per-lane scalar SLOW path costs ~18 us for such a block -- profiles/gemm_trace_r01_fine.txt,
+// "SM 77" -- and with M = 1872 = 14.6 tiles it sat on the tail of every denoiser GEMM.)
 template <int ACT>
-TTB_DEVINL void epi_chunk_fast(const uint32_t* r, int nb, int m_base, int lane, long long bz, const GemmEpilogue& ep,
-                               uint32_t scratch) {
+TTB_DEVINL void epi_chunk_fast(const uint32_t* r, int nb, int m_base, int rows_valid, int lane, long long bz,
+                               const GemmEpilogue& ep, uint32_t scratch) {
   const uint32_t wrow = scratch + (uint32_t)lane * (EPI_PITCH * 4);
+  const bool GN = ep.gn_part != nullptr;
   float v[32];
   if (ep.bias) {
 #pragma unroll
@@ -109,6 +113,7 @@ TTB_DEVINL void epi_chunk_fast(const uint32_t* r, int nb, int m_base, int lane, 
       const int rr = it * 8 + rr0;
       const float4 o = lds128(scratch + (uint32_t)(rr * EPI_PITCH + c) * 4);
       const long long m = m_base + rr;
+      if (rr >= rows_valid) continue;
       if (ep.out_bf16)
         *reinterpret_cast<uint2*>(ep.out_bf16 + bz * ep.outb_bstride + m * ep.ldob + col) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
       if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + bz * ep.outf_bstride + m * ep.ldo + col) = o;
@@ -123,7 +128,10 @@ TTB_DEVINL void epi_chunk_fast(const uint32_t* r, int nb, int m_base, int lane, 
   if (ep.residual) {
     const float* rp = ep.residual + bz * ep.res_bstride + (long long)(m_base + rr0) * ep.ldr + col;
 #pragma unroll
-    for (int it = 0; it < 8; ++it) rs[it] = *reinterpret_cast<const float4*>(rp + (long long)it * 4 * ep.ldr);
+    for (int it = 0; it < 8; ++it) {
+      if (it * 4 + rr0 < rows_valid) rs[it] = *reinterpret_cast<const float4*>(rp + (long long)it * 4 * ep.ldr);
+      else rs[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k)
@@ -137,13 +145,16 @@ TTB_DEVINL void epi_chunk_fast(const uint32_t* r, int nb, int m_base, int lane, 
     float4 o = lds128(scratch + (uint32_t)(rr * EPI_PITCH + c) * 4);
     if (ep.residual) { o.x += rs[it].x; o.y += rs[it].y; o.z += rs[it].z; o.w += rs[it].w; }
     const long long m = m_base + rr;
+    if (rr >= rows_valid) continue;
     if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + bz * ep.outf_bstride + m * ep.ldo + col) = o;
     if (ep.out_bf16)
       *reinterpret_cast<uint2*>(ep.out_bf16 + bz * ep.outb_bstride + m * ep.ldob + col) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
-    gs += (o.x + o.y) + (o.z + o.w);
-    gq += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+    if (GN) {
+      gs += (o.x + o.y) + (o.z + o.w);
+      gq += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+    }
   }
-  if (ep.gn_part) epi_gn_store(gs, gq, nb, m_base, lane, bz, ep);
+  if (GN) epi_gn_store(gs, gq, nb, m_base, lane, bz, ep);
   __syncwarp();                                      // scratch is reused by the next chunk
 }
 
@@ -193,7 +204,8 @@ template <int BN, int ACT>
 TTB_DEVINL void gemm_epilogue_tile(uint32_t taddr, int n0, int N, int m_base, int M, int lane, long long bz,
                                    const GemmEpilogue& ep, uint32_t scratch, uint64_t* release_bar) {
   constexpr int NCH = BN / 32;
-  const bool rows_full = epi_flags(ep).aligned && m_base + 32 <= M;
+  const bool aligned = epi_flags(ep).aligned;
+  const int rows_valid = min(32, M - m_base);        // warp-uniform; <= 0: this warp's rows are all past M
   // rolled on purpose: one chunk's worth of code and registers (the 128-wide kernel must stay <= 168 registers for
   // two CTAs per SM); the co-resident warps cover the tcgen05.ld latency
 #pragma unroll 1
@@ -203,12 +215,13 @@ TTB_DEVINL void gemm_epilogue_tile(uint32_t taddr, int n0, int N, int m_base, in
     tmem_ld_32x32b_x32(taddr + (uint32_t)ch * 32, r);
     tmem_ld_wait_dep(r);
     if (release_bar && ch == NCH - 1) { tc_fence_before(); mbar_arrive(release_bar); }
-    if (nb >= N) continue;                           // warp-uniform
-    if (rows_full && nb + 32 <= N) epi_chunk_fast<ACT>(r, nb, m_base, lane, bz, ep, scratch);
-    else {
+    if (nb >= N || rows_valid <= 0) continue;        // warp-uniform
+    if (aligned && nb + 32 <= N) {
+      epi_chunk_fast<ACT>(r, nb, m_base, rows_valid, lane, bz, ep, scratch);
+    } else {
       float gs = 0.f, gq = 0.f;                      // rows past M contribute nothing
       epi_chunk_slow<ACT>(r, nb, N, m_base + lane, M, bz, ep, gs, gq);
-      if (ep.gn_part && m_base < M) epi_gn_store(gs, gq, nb, m_base, lane, bz, ep);
+      if (ep.gn_part) epi_gn_store(gs, gq, nb, m_base, lane, bz, ep);
     }
   }
 }
