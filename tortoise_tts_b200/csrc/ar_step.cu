@@ -99,11 +99,19 @@ TTB_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P1;\n\t"
+#if TTB_MBAR_HINT_NS > 0
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"    // parked up to the hint (common.cuh)
+      "selp.u32 %0, 1, 0, P1;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)TTB_MBAR_HINT_NS)
+      : "memory");
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, P1;\n\t}\n"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 
@@ -671,7 +679,10 @@ TTB_DEVINL void mma_chunk(MmaState& st, const uint32_t* qb, uint32_t kt, uint32_
   }
 }
 
-TTB_DEVINL void attn_phase_mma(const AsParams& p, int layer, uint8_t* data, AsCtrl* ctrl, AsRole& rl) {
+// `wait_pdl`: the caller has NOT yet executed griddepcontrol.wait (ar_attn_only_kernel under programmatic dependent
+// launch): the prompt prefix and the first candidate tiles are requested first -- the caches were written by earlier
+// steps / this step's earlier kernels, only q and the new K / V come from the c_attn GEMM this launch depends on.
+TTB_DEVINL void attn_phase_mma(const AsParams& p, int layer, uint8_t* data, AsCtrl* ctrl, AsRole& rl, bool wait_pdl = false) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* err = &p.state->reserved[0];
   const int B = p.B, H = p.H, P = p.P, Nmax = p.Nmax, D = p.H * 64;
@@ -698,6 +709,26 @@ TTB_DEVINL void attn_phase_mma(const AsParams& p, int layer, uint8_t* data, AsCt
       }
     }
     const int sub = warp % p.team;
+    const int nch = (nold + 15) / 16;
+    // first NS tiles of candidate bb's stream into this warp's ring (lane 0). All stages are free whenever this is
+    // called: at the start of the unit, or after the last tile of the previous item was consumed.
+    auto issue_head = [&](int bb) {
+      const __nv_bfloat16* cbb = ckv_l + ((long long)bb * H + h) * Nmax * 128;
+      const int it = (layer * B + bb) * H + h;
+      for (int s = 0; s < NS; ++s) {
+        const int c = sub + s * p.team;
+        if (c < nch) {
+          mbar_arrive_expect_tx(&ctrl->ring_bar[warp][s], (uint32_t)CHUNK_BYTES);
+          if (p.attn_impl == 2) {
+            bulk_g2s(ring + s * CHUNK_BYTES, cbb + (long long)c * 16 * 128, (uint32_t)CHUNK_BYTES, &ctrl->ring_bar[warp][s]);
+          } else {
+            tma_load_4d(ring + s * CHUNK_BYTES, map_c, &ctrl->ring_bar[warp][s], 0, 0, c * 16, it);
+            tma_load_4d(ring + s * CHUNK_BYTES + 2048, map_c, &ctrl->ring_bar[warp][s], 0, 1, c * 16, it);
+          }
+        }
+      }
+    };
+    bool head_issued = false;        // the stream of this round's item was started during the previous round
     for (int r0 = b_begin; r0 < b_end; r0 += p.ipr) {
       const int b = r0 + warp / p.team;
       const bool valid = (warp < p.ipr * p.team) && (b < b_end);
@@ -707,6 +738,9 @@ TTB_DEVINL void attn_phase_mma(const AsParams& p, int layer, uint8_t* data, AsCt
       for (int db = 0; db < 4; ++db)
 #pragma unroll
         for (int i = 0; i < 4; ++i) st.acc[db][i] = 0.f;
+      // the KV stream first (it needs addresses only), then q: the q loads overlap the first tiles' latency
+      if (valid && !head_issued && lane == 0) issue_head(b);
+      if (wait_pdl) { pdl_wait(); wait_pdl = false; }
       if (valid) {
         const __nv_bfloat16* qrow = p.qkv + (long long)b * 3 * D + h * 64;
         // q as the B operand of the score MMA: column 0 <-> lanes 0-3; b0 = dims 16 ks + 2 lane (+1), b1 = + 8
@@ -719,21 +753,6 @@ TTB_DEVINL void attn_phase_mma(const AsParams& p, int layer, uint8_t* data, AsCt
         }
         __nv_bfloat16* cb = ckv_l + ((long long)b * H + h) * Nmax * 128;
         const int item = (layer * B + b) * H + h;          // 4th coordinate of the candidate-cache tensor map
-        const int nch = (nold + 15) / 16;
-        if (lane == 0) {
-          for (int s = 0; s < NS; ++s) {
-            const int c = sub + s * p.team;
-            if (c < nch) {
-              mbar_arrive_expect_tx(&ctrl->ring_bar[warp][s], (uint32_t)CHUNK_BYTES);
-              if (p.attn_impl == 2) {
-                bulk_g2s(ring + s * CHUNK_BYTES, cb + (long long)c * 16 * 128, (uint32_t)CHUNK_BYTES, &ctrl->ring_bar[warp][s]);
-              } else {
-                tma_load_4d(ring + s * CHUNK_BYTES, map_c, &ctrl->ring_bar[warp][s], 0, 0, c * 16, item);
-                tma_load_4d(ring + s * CHUNK_BYTES + 2048, map_c, &ctrl->ring_bar[warp][s], 0, 1, c * 16, item);
-              }
-            }
-          }
-        }
         if (sub == 0) {
           // the new token: append K / V to the cache, account for it from registers (SIMT, once per item)
           const uint32_t kq = __ldcg(reinterpret_cast<const uint32_t*>(qrow + D) + lane);      // dims 2 lane, 2 lane + 1
@@ -775,6 +794,11 @@ TTB_DEVINL void attn_phase_mma(const AsParams& p, int layer, uint8_t* data, AsCt
           }
           if (++s == NS) s = 0;
         }
+        // every stage is free again: start the stream of this warp's NEXT item now, so that its first tiles travel
+        // while the prompt part, the merge and the output of this item are computed (the rounds of all warps and SMs
+        // run in step: without this the memory system idles ~6 us per round, tools/dbg/kvstream_probe2.cu)
+        head_issued = (b + p.ipr < b_end);
+        if (head_issued && lane == 0) issue_head(b + p.ipr);
         mbar_wait_to(&ctrl->prefix_bar, rl.prefix_par, err);
         for (int c = sub; c < npc; c += p.team) {
           const uint32_t kt = smem_u32(prefix_s + c * CHUNK_BYTES);
@@ -1018,12 +1042,13 @@ __global__ void __launch_bounds__(AS_THREADS, 1) ar_attn_only_kernel(const __gri
     fence_barrier_init();
   }
   __syncthreads();
-  pdl_wait();                      // qkv belongs to the c_attn GEMM before this point (TTB_PDL=1)
+  if (p.attn_impl < 1) pdl_wait();  // qkv belongs to the c_attn GEMM before this point (TTB_PDL=1); the tensor-core form
+                                    // waits inside, after it has requested its first cache tiles
   AsRole rl;
   rl.stage = 0; rl.phase = 0; rl.acc_par = 0; rl.prefix_par = 0; rl.bar_target = 0;
   rl.ring_par[0] = rl.ring_par[1] = rl.ring_par[2] = rl.ring_par[3] = 0;
   const int l = p.layer_begin;
-  if (p.attn_impl >= 1) attn_phase_mma(p, l, data, ctrl, rl);
+  if (p.attn_impl >= 1) attn_phase_mma(p, l, data, ctrl, rl, true);
   else if (p.ring_cp == 8) attn_phase<8>(p, l, data, ctrl, rl);
   else attn_phase<16>(p, l, data, ctrl, rl);
   pdl_launch_dependents();
