@@ -776,7 +776,19 @@ TTB_DEVINL void attn_phase_mma(const AsParams& p, int layer, uint8_t* data, AsCt
           }
         }
         int s = 0;
+        // The prompt part (npc chunks already in shared memory, the same for every candidate of this head) is worked
+        // off one chunk at a time BEFORE each wait for a candidate tile: the warp would otherwise sit idle at the ring
+        // barrier (a tile takes ~1.7 us to arrive, a chunk ~0.2 us to compute), and doing the prompt part after the
+        // stream left the memory system idle for ~2 us per round.
+        int pc = sub;
+        bool prefix_ready = false;
         for (int c_use = sub; c_use < nch; c_use += p.team) {
+          if (pc < npc) {
+            if (!prefix_ready) { mbar_wait_to(&ctrl->prefix_bar, rl.prefix_par, err); prefix_ready = true; }
+            const uint32_t kp = smem_u32(prefix_s + pc * CHUNK_BYTES);
+            mma_chunk(st, qb, kp, kp + 2048, min(16, P - pc * 16), lane);
+            pc += p.team;
+          }
           mbar_wait_to(&ctrl->ring_bar[warp][s], rl.ring_par[s], err);
           rl.ring_par[s] ^= 1;
           const uint32_t kt = smem_u32(ring + s * CHUNK_BYTES);
@@ -799,8 +811,8 @@ TTB_DEVINL void attn_phase_mma(const AsParams& p, int layer, uint8_t* data, AsCt
         // run in step: without this the memory system idles ~6 us per round, tools/dbg/kvstream_probe2.cu)
         head_issued = (b + p.ipr < b_end);
         if (head_issued && lane == 0) issue_head(b + p.ipr);
-        mbar_wait_to(&ctrl->prefix_bar, rl.prefix_par, err);
-        for (int c = sub; c < npc; c += p.team) {
+        if (!prefix_ready) mbar_wait_to(&ctrl->prefix_bar, rl.prefix_par, err);
+        for (int c = pc; c < npc; c += p.team) {             // what is left of the prompt part (long prompts, early steps)
           const uint32_t kt = smem_u32(prefix_s + c * CHUNK_BYTES);
           mma_chunk(st, qb, kt, kt + 2048, min(16, P - c * 16), lane);
         }
