@@ -10,7 +10,7 @@ import os
 import pytest
 import torch
 
-from gpu_util import report
+from gpu_util import check_sampled_mel, report
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "small_v1.pt")
@@ -249,16 +249,12 @@ def test_diffusion_small_vs_golden(small):
     # (2) the full sampling loop. The DDPM update multiplies the eps error by sqrt(1/abar_t - 1) (153 at t=3999,
     # utils/diffusion.py:420-425) before the clamp, so with random weights the bf16 operand rounding alone moves the
     # final mel by ~1.0 of its 13.8 range (measured by running the fp32 oracle with bf16-rounded GEMM operands,
-    # tests/test_host_orchestration.py). Bound = 1.5x that drift; graph and eager paths must agree exactly.
+    # tests/test_host_orchestration.py). Bounds: gpu_util.check_sampled_mel; graph and eager paths must agree exactly.
     mels = []
     for use_graph in (False, True):
         mel = eng.sample(g["diff_latents"][0], g["diff_cond"][0], g["diff_iters"], g["diff_noise0"][0],
                          g["diff_step_noise"][:, 0], cond_free=True, cond_free_k=2.0, use_graph=use_graph).cpu()
-        err = (mel - g["diff_mel"][0]).abs().max().item()
-        rms = (mel - g["diff_mel"][0]).pow(2).mean().sqrt().item()
-        report("diffusion mel small max (range 13.8) graph=%d" % use_graph, err)
-        report("diffusion mel small rms graph=%d" % use_graph, rms)
-        assert err < 1.5 and rms < 0.3
+        check_sampled_mel("diffusion mel small graph=%d" % use_graph, mel, g["diff_mel"][0])
         mels.append(mel)
     assert (mels[0] - mels[1]).abs().max().item() < 1e-3
 
@@ -360,11 +356,7 @@ def test_tts_end_to_end_small(small):
         want_mel = od.spectrogram_diffusion(sds["diffusion"], cfg, lat_full[:, :n_lat], cl[1], noise0.unsqueeze(0),
                                             step_noise.unsqueeze(1), 4, cond_free=False)[0]
     got_mel = dbg["mel"][j].cpu()
-    err = (got_mel - want_mel).abs().max().item()
-    rms = (got_mel - want_mel).pow(2).mean().sqrt().item()
-    report("e2e small mel max (range 13.8)", err)
-    report("e2e small mel rms", rms)
-    assert err < 1.5 and rms < 0.3          # same bound as the sampled-mel stage test
+    check_sampled_mel("e2e small mel", got_mel, want_mel)      # same bound as the sampled-mel stage test
     outs = tts.tts_with_preset("unused", preset="ultra_fast", k=2, **kw)
     assert isinstance(outs, list) and len(outs) == 2
     with pytest.raises(KeyError):

@@ -12,6 +12,8 @@
 //                 accumulate o = o*corr + O_j in registers (no TMEM read-modify-write).
 // Replaces the materialised [H, T, T] score tensors of QKVAttentionLegacy (arch_util.py:60-77), HF GPT2Attention._attn
 // and xtransformers Attention (xtransformers.py:660-712).
+#include <type_traits>
+
 #include "common.cuh"
 #include "ttb_internal.h"
 
@@ -200,6 +202,11 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
+      // The rest of the tile is instantiated once per tile class: with one shared body the score registers of the two
+      // classes had to agree at the join, which cost the common (fast) class 64 register moves per tile (SASS of
+      // profiles/ncu_r02/fa_dbuf.ncu-rep: 42 IMAD.MOV + 22 MOV in a 100-instruction max block).
+      auto tile_body = [&](auto fast_tag) {
+      constexpr bool FAST = decltype(fast_tag)::value;
       // S_j ready (without DBUF this also means that every earlier MMA, incl. P V of tile j-1, has retired)
       mbar_wait(&s_full[DBUF ? (j & 1) : 0], DBUF ? ((j >> 1) & 1) : (j & 1));
       tc_fence_after();
@@ -208,7 +215,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       tmem_ld_32x32b_x32(tmem_s + (DBUF ? (uint32_t)((j & 1) * 64) : 0u) + lane_base + 32, r1);
       tmem_ld_wait();
       float mx = -INFINITY;
-      if (fast) {
+      if constexpr (FAST) {
         float mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // 4 independent chains (ILP)
 #pragma unroll
         for (int c = 0; c < 32; ++c) mq[c & 3] = fmaxf(mq[c & 3], fmaxf(__uint_as_float(r0[c]), __uint_as_float(r1[c])));
@@ -249,7 +256,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       float psum = 0.f;
       uint32_t pk[32];
-      if (fast) {
+      if constexpr (FAST) {
         const float cm = cb - m_use;
         float ps[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -279,6 +286,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(p_full);
+      };
+      if (fast) tile_body(std::true_type{}); else tile_body(std::false_type{});
     }
     // all P V products have been issued; wait for the last one and read the accumulated O row
     mbar_wait(o_full, (ntiles - 1) & 1);
