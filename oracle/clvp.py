@@ -25,8 +25,9 @@ def _rotary(t, freqs):
     return t * freqs.cos() + rot * freqs.sin()
 
 
-def encoder(sd, prefix, x, depth, heads):
-    """x [B, n, D] -> [B, n, D] (after the final LayerNorm)."""
+def encoder(sd, prefix, x, depth, heads, wrap="wrap."):
+    """x [B, n, D] -> [B, n, D] (after the final LayerNorm). `wrap`: "wrap." for the CheckpointedXTransformerEncoder CLVP
+    uses (arch_util.py:334-373), "" for a plain ContinuousTransformerWrapper (CVVP, cvvp.py:23-36)."""
     B, n, D = x.shape
     hd = D // heads
     inv_freq = sd[prefix + "attn_layers.rotary_pos_emb.inv_freq"]
@@ -37,20 +38,20 @@ def encoder(sd, prefix, x, depth, heads):
     for l in range(depth):
         a = f"{prefix}attn_layers.layers.{2 * l}."
         h = _rmsnorm(x, sd[a + "0.0.g"])
-        q = h @ sd[a + "1.wrap.to_q.weight"].t()
-        k = h @ sd[a + "1.wrap.to_k.weight"].t()
-        v = h @ sd[a + "1.wrap.to_v.weight"].t()
+        q = h @ sd[a + "1." + wrap + "to_q.weight"].t()
+        k = h @ sd[a + "1." + wrap + "to_k.weight"].t()
+        v = h @ sd[a + "1." + wrap + "to_v.weight"].t()
         q, k, v = (t.view(B, n, heads, hd).transpose(1, 2) for t in (q, k, v))
         q, k, v = (torch.cat((_rotary(t[..., :rd], freqs), t[..., rd:]), dim=-1) for t in (q, k, v))
         w = torch.softmax((q @ k.transpose(-1, -2)) * (hd ** -0.5), dim=-1)
         o = (w @ v).transpose(1, 2).reshape(B, n, D)
-        x = x + (o @ sd[a + "1.wrap.to_out.weight"].t() + sd[a + "1.wrap.to_out.bias"])
+        x = x + (o @ sd[a + "1." + wrap + "to_out.weight"].t() + sd[a + "1." + wrap + "to_out.bias"])
         fpre = f"{prefix}attn_layers.layers.{2 * l + 1}."
         h = _rmsnorm(x, sd[fpre + "0.0.g"])
-        proj = h @ sd[fpre + "1.wrap.net.0.proj.weight"].t() + sd[fpre + "1.wrap.net.0.proj.bias"]
+        proj = h @ sd[fpre + "1." + wrap + "net.0.proj.weight"].t() + sd[fpre + "1." + wrap + "net.0.proj.bias"]
         u, g = proj.chunk(2, dim=-1)
         h = u * F.gelu(g)
-        x = x + (h @ sd[fpre + "1.wrap.net.3.weight"].t() + sd[fpre + "1.wrap.net.3.bias"])
+        x = x + (h @ sd[fpre + "1." + wrap + "net.3.weight"].t() + sd[fpre + "1." + wrap + "net.3.bias"])
     return F.layer_norm(x, (D,), sd[prefix + "norm.weight"], sd[prefix + "norm.bias"], 1e-5)
 
 

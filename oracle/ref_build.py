@@ -39,4 +39,9 @@ def build_reference_models(cfg, sds, kv_cache=True):
     voc = UnivNetGenerator().cpu()
     voc.load_state_dict(sds["vocoder"], strict=True)
     voc.eval(inference=True)
-    return {"autoregressive": ar, "diffusion": diff, "clvp": clvp, "vocoder": voc, "missing": missing}
+    from tortoise.models.cvvp import CVVP
+    cvvp = CVVP(model_dim=cfg.cvvp_dim, transformer_heads=cfg.cvvp_heads, dropout=0, mel_codes=cfg.clvp_speech_tokens,
+                conditioning_enc_depth=cfg.cvvp_depth, cond_mask_percentage=0, speech_enc_depth=cfg.cvvp_depth,
+                speech_mask_percentage=0, latent_multiplier=1).eval()          # api.py:254-255
+    cvvp.load_state_dict(sds["cvvp"], strict=True)
+    return {"autoregressive": ar, "diffusion": diff, "clvp": clvp, "vocoder": voc, "cvvp": cvvp, "missing": missing}

@@ -366,6 +366,69 @@ def test_tts_end_to_end_small(small):
 
 
 @pytest.mark.gpu
+def test_tts_cvvp_amount_blend(small):
+    """tts(voice_samples=..., cvvp_amount=a) ranks by cvvp * a + clvp * (1 - a) (api.py:450-472): the scores the facade
+    ranked with against the oracle's CLVP and CVVP on the same codes and the same conditioning mels; a = 1 uses CVVP alone;
+    conditioning_latents without clips falls back to CLVP as the reference does (auto_conds is None)."""
+    from tortoise_tts_b200.api import TextToSpeech
+    from oracle import clvp as oclvp, cvvp as ocvvp
+    cfg, sds, g = small
+    tts = TextToSpeech(state_dicts=sds, config=cfg, kv_cache=True)
+    torch.manual_seed(31)
+    clips = [(torch.randn(1, n) * 0.1).clamp(-1, 1) for n in (90000, 120000)]      # shorter than 132300: padded, no random crop
+    kw = dict(text_tokens=TEXT[:-1], use_deterministic_seed=5, max_mel_tokens=24, num_autoregressive_samples=8,
+              diffusion_iterations=2, verbose=False)
+    auto_conds = tts.get_conditioning_latents(clips, return_mels=True)[2]
+    assert auto_conds.shape[:3] == (1, 2, 80)
+    toks = TEXT[:-1] + [0]
+    for amount in (0.5, 1.0):
+        tts.debug_capture = True
+        tts.tts_with_preset("unused", preset="ultra_fast", voice_samples=clips, cvvp_amount=amount, **kw)
+        dbg = tts.last_debug
+        tts.debug_capture = False
+        codes = dbg["codes"].cpu().long()
+        with torch.no_grad():
+            cl = oclvp.scores(sds["clvp"], cfg, torch.tensor(toks), codes)
+            cv = ocvvp.scores(sds["cvvp"], cfg, auto_conds.cpu(), codes)
+        want = cv if amount == 1.0 else cv * amount + cl * (1 - amount)
+        e = (dbg["scores"].cpu() - want).abs().max().item()
+        report("e2e small CLVP/CVVP blend scores abs, cvvp_amount=%.1f" % amount, e)
+        assert e < 0.03
+    latents = tts.get_conditioning_latents(clips)
+    tts.debug_capture = True
+    tts.tts_with_preset("unused", preset="ultra_fast", conditioning_latents=latents, cvvp_amount=0.5, **kw)
+    codes = tts.last_debug["codes"].cpu().long()
+    with torch.no_grad():
+        cl = oclvp.scores(sds["clvp"], cfg, torch.tensor(toks), codes)
+    assert (tts.last_debug["scores"].cpu() - cl).abs().max().item() < 0.03
+    tts.debug_capture = False
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["small", "full"])
+def test_cvvp_scores(which):
+    """SURVEY 8f row 4 (cvvp.py:108-124 as accumulated in api.py:464-468): scores of every candidate against two
+    conditioning clips vs oracle/cvvp.py; `full` = the reference's CVVP(512, 8 heads, depth 8) on 500 codes."""
+    from tortoise_tts_b200.config import ModelConfig
+    from tortoise_tts_b200.synth import synth_cvvp
+    from tortoise_tts_b200.cvvp_engine import CVVPEngine
+    from oracle import cvvp as oc
+    cfg = ModelConfig.small() if which == "small" else ModelConfig.full()
+    sd = synth_cvvp(cfg, 0)
+    torch.manual_seed(21)
+    B, L, Tm = (6, 60, 151) if which == "small" else (4, 500, 517)
+    codes = torch.randint(0, 8192, (B, L))
+    auto_conds = torch.randn(1, 2, 80, Tm) * 2 - 4
+    got = CVVPEngine(sd, cfg).scores(auto_conds, codes, chunk=4).cpu()
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad(), torch.device("cuda"):
+        want = oc.scores(sdc, cfg, auto_conds.cuda(), codes.cuda()).cpu()
+    e = (got - want).abs().max().item()
+    report("CVVP scores %s abs (scale e = 2.7)" % which, e)
+    assert e < 0.03
+
+
+@pytest.mark.gpu
 def test_tts_long_concatenates_chunks(small):
     """≙ read.py:44-85: every chunk is synthesised with the same seed and latents; the result is the concatenation."""
     from tortoise_tts_b200.api import TextToSpeech

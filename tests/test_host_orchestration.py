@@ -110,6 +110,27 @@ def test_diffusion_engine_fused_groupnorm_statistics(env):
     assert _rel(outs[1][0], outs[0][0]) < 0.01 and _rel(outs[1][1], outs[0][1]) < 0.01
 
 
+def test_cvvp_engine(env):
+    """CVVP re-ranker: strided conv front-end, both CollapsingTransformers, pooling commuted with the
+    last 1x1 conv, clip average folded into one latent -- against oracle/cvvp.py, kernels emulated."""
+    from tortoise_tts_b200.cvvp_engine import CVVPEngine
+    from oracle import cvvp as oc
+    cfg, sds, g = env
+    torch.manual_seed(9)
+    codes = torch.randint(0, 8192, (5, 37))
+    auto_conds = torch.randn(1, 2, 80, 151) * 2 - 4
+    eng = CVVPEngine(sds["cvvp"], cfg, device="cpu")
+    with torch.no_grad():
+        want = oc.scores(sds["cvvp"], cfg, auto_conds, codes)
+        want_c = oc.cond_latent(sds["cvvp"], cfg, auto_conds[:, 1])
+    got_c = eng.cond_latent(auto_conds[0, 1])
+    assert (got_c - want_c).abs().max().item() < 0.03
+    got = eng.scores(auto_conds, codes, chunk=2)
+    assert (got - want).abs().max().item() < 0.03, (got, want)
+    with pytest.raises(IndexError):
+        eng.scores(auto_conds, torch.full((1, 4), 8192))
+
+
 def test_vocoder_engine(env):
     from tortoise_tts_b200.vocoder_engine import VocoderEngine
     cfg, sds, g = env

@@ -152,6 +152,23 @@ def test_clvp_scores(small):
     assert (got - want).abs().max().item() < 1e-5
 
 
+def test_cvvp_scores(small):
+    """oracle/cvvp.py == CVVP.forward(mel_cond, codes, return_loss=False) accumulated over the conditioning clips as
+    api.py:464-468 does (strict=True load of the synthetic cvvp.pth checks the key layout too)."""
+    from oracle import cvvp
+    cfg, sds, m = small
+    torch.manual_seed(15)
+    codes = torch.randint(0, 8192, (3, 23))
+    auto_conds = torch.randn(1, 2, 80, 131) * 2 - 4           # [1, n_clips, 80, T] as get_conditioning_latents returns
+    with torch.no_grad():
+        acc = 0
+        for cl in range(auto_conds.shape[1]):
+            acc = acc + m["cvvp"](auto_conds[:, cl].repeat(3, 1, 1), codes, return_loss=False)
+        want = acc / auto_conds.shape[1]
+        got = cvvp.scores(sds["cvvp"], cfg, auto_conds, codes)
+    assert (got - want).abs().max().item() < 1e-5
+
+
 def test_diffusion_forward_and_loop(small):
     from oracle import diffusion as od
     from tortoise.api import load_discrete_vocoder_diffuser, do_spectrogram_diffusion

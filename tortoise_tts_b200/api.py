@@ -230,6 +230,8 @@ class TextToSpeech:
                                                if state_dicts.get("mel_norms", None) is not None else _default_mel_norms())
         self._rlg_sd = (state_dicts.get("rlg_auto"), state_dicts.get("rlg_diffuser"))
         self.rlg_auto = self.rlg_diffusion = None
+        self._cvvp_sd = state_dicts.get("cvvp")
+        self.cvvp = None                 # the CVVP model is only loaded if used (api.py:234,252-256)
         self.last_timings = {}
         self.debug_capture = False
         self.last_debug = None
@@ -245,6 +247,14 @@ class TextToSpeech:
                 diffusion_latent, diffusion_conds = self.conditioning.diffusion_latent(voice_samples, return_mels=True)
                 return auto_latent, diffusion_latent, auto_conds, diffusion_conds
             return self.conditioning.ar_latent(voice_samples), self.conditioning.diffusion_latent(voice_samples)
+
+    def load_cvvp(self):
+        """≙ api.py:252-256 (cvvp.pth, lazily loaded)."""
+        from .cvvp_engine import CVVPEngine
+        sd = self._cvvp_sd
+        if sd is None:
+            sd = torch.load(get_model_path("cvvp.pth", self.models_dir), map_location="cpu")
+        self.cvvp = CVVPEngine(sd, self.cfg, self.device)
 
     def get_random_conditioning_latents(self):
         """≙ api.py:301-309 (rlg_auto.pth / rlg_diffuser.pth, lazily loaded)."""
@@ -322,14 +332,15 @@ class TextToSpeech:
             repetition_penalty=2.0, top_p=.8, max_mel_tokens=500, cvvp_amount=.0, diffusion_iterations=100,
             cond_free=True, cond_free_k=2, diffusion_temperature=1.0, text_tokens=None, top_k=50, **hf_generate_kwargs):
         """≙ TextToSpeech.tts (api.py:334-597). `text_tokens` (list of BPE ids) may be given instead of `text`."""
-        if cvvp_amount != 0:
-            raise NotImplementedError("CVVP is out of scope of this engine (disabled by default in the reference)")
         if hf_generate_kwargs:
             raise TypeError(f"unsupported generate kwargs: {sorted(hf_generate_kwargs)}")
         seed = self.deterministic_state(seed=use_deterministic_seed)
         # api.py:395-401 (after the seeding, so that the random crop / random voice follow use_deterministic_seed)
+        auto_conds = None                 # the conditioning MELs: only known when the clips themselves are given
         if voice_samples is not None:
-            conditioning_latents = self.get_conditioning_latents(voice_samples, return_mels=False)
+            auto_conditioning, diffusion_conditioning, auto_conds, _ = self.get_conditioning_latents(voice_samples,
+                                                                                                   return_mels=True)
+            conditioning_latents = (auto_conditioning, diffusion_conditioning)
         elif conditioning_latents is None:
             conditioning_latents = self.get_random_conditioning_latents()
         dev = self.device
@@ -359,7 +370,17 @@ class TextToSpeech:
             trim = torch.empty(nb, dtype=torch.int32, device=dev)
             lib.ar_fix_codes(codes, nb, L, self.cfg.stop_mel_token, trim)
             ev[1].record()
-            scores = self.clvp.scores(toks, codes)
+            # api.py:450-472: CLVP, CVVP (needs the conditioning mels, i.e. voice_samples) or their blend. cvvp_amount = 1
+            # without voice_samples leaves `clvp_out` undefined in the reference; CLVP alone is used here.
+            use_cvvp = cvvp_amount > 0 and auto_conds is not None
+            if use_cvvp and self.cvvp is None:
+                self.load_cvvp()
+            scores = None
+            if cvvp_amount != 1 or not use_cvvp:
+                scores = self.clvp.scores(toks, codes)
+            if use_cvvp:
+                cv = self.cvvp.scores(auto_conds, codes)
+                scores = cv if cvvp_amount == 1 else cv * cvvp_amount + scores * (1 - cvvp_amount)
             scores, codes = parallel.gather_candidates(scores, codes, B)
             best = torch.topk(scores, k=k).indices
             best_codes = codes[best].contiguous()

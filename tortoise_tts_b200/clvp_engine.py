@@ -21,25 +21,49 @@ def _f(t, dev):
 
 
 class _Encoder:
-    def __init__(self, sd, prefix, depth, dev):
+    """Weights of one x-transformers Encoder. `wrap`: "wrap." for CLVP's CheckpointedXTransformerEncoder keys
+    (arch_util.py:334-373), "" for a plain ContinuousTransformerWrapper (CVVP, cvvp.py:23-36)."""
+
+    def __init__(self, sd, prefix, depth, dev, wrap="wrap."):
         self.layers = []
         for l in range(depth):
             a = f"{prefix}attn_layers.layers.{2 * l}."
             f = f"{prefix}attn_layers.layers.{2 * l + 1}."
-            wq, wk, wv = (sd[a + f"1.wrap.{n}.weight"] for n in ("to_q", "to_k", "to_v"))
-            w1, b1 = sd[f + "1.wrap.net.0.proj.weight"], sd[f + "1.wrap.net.0.proj.bias"]
+            wq, wk, wv = (sd[a + f"1.{wrap}{n}.weight"] for n in ("to_q", "to_k", "to_v"))
+            w1, b1 = sd[f + f"1.{wrap}net.0.proj.weight"], sd[f + f"1.{wrap}net.0.proj.bias"]
             inner = w1.shape[0] // 2
+            self.inner = inner
             # GLU: x, gate = proj(x).chunk(2) (xtransformers.py:435-437) -> interleave rows (u0,g0,u1,g1,...) so the
             # GEMM epilogue can form u*gelu(g) from adjacent accumulator columns
             w1i = torch.stack([w1[:inner], w1[inner:]], dim=1).reshape(2 * inner, -1)
             b1i = torch.stack([b1[:inner], b1[inner:]], dim=1).reshape(2 * inner)
             self.layers.append(dict(
                 g_attn=_f(sd[a + "0.0.g"], dev), wqkv=_bf(torch.cat([wq, wk, wv], dim=0), dev),
-                wout=_bf(sd[a + "1.wrap.to_out.weight"], dev), bout=_f(sd[a + "1.wrap.to_out.bias"], dev),
+                wout=_bf(sd[a + f"1.{wrap}to_out.weight"], dev), bout=_f(sd[a + f"1.{wrap}to_out.bias"], dev),
                 g_ff=_f(sd[f + "0.0.g"], dev), w1=_bf(w1i, dev), b1=_f(b1i, dev),
-                w2=_bf(sd[f + "1.wrap.net.3.weight"], dev), b2=_f(sd[f + "1.wrap.net.3.bias"], dev)))
+                w2=_bf(sd[f + f"1.{wrap}net.3.weight"], dev), b2=_f(sd[f + f"1.{wrap}net.3.bias"], dev)))
         self.norm_g = _f(sd[prefix + "norm.weight"], dev)
         self.norm_b = _f(sd[prefix + "norm.bias"], dev)
+
+
+def encoder_layers(enc, x, nseq, T, D, H, dev):
+    """The Encoder's layer stack on the fp32 residual stream x [nseq*T, D], in place (everything but the final
+    LayerNorm): pre-RMSNorm attention with rotary 32 on q / k / v, pre-RMSNorm GEGLU feed-forward
+    (xtransformers.py:906-1013 as configured in clvp.py:54-83 and cvvp.py:23-36)."""
+    M = nseq * T
+    a = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
+    qkv = torch.empty(M, 3 * D, dtype=torch.bfloat16, device=dev)
+    o = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
+    h = torch.empty(M, enc.inner, dtype=torch.bfloat16, device=dev)
+    for lw in enc.layers:
+        lib.rmsnorm(x, M, D, lw["g_attn"], a)
+        lib.gemm(a, lw["wqkv"], M=M, N=3 * D, K=D, out_bf16=qkv)
+        lib.clvp_rotary(qkv, nseq, T, H)
+        lib.attention(qkv, o, nseq=nseq, T=T, H=H, ld=3 * D, ldo=D, k_off=D, v_off=2 * D, scale=0.125)
+        lib.gemm(o, lw["wout"], M=M, N=D, K=D, bias=lw["bout"], residual=x, out_f32=x)
+        lib.rmsnorm(x, M, D, lw["g_ff"], a)
+        lib.gemm(a, lw["w1"], M=M, N=2 * enc.inner, K=D, bias=lw["b1"], act=lib.ACT_GEGLU, out_bf16=h)
+        lib.gemm(h, lw["w2"], M=M, N=D, K=enc.inner, bias=lw["b2"], residual=x, out_f32=x)
 
 
 class CLVPEngine:
@@ -58,23 +82,11 @@ class CLVPEngine:
 
     def _encode(self, enc, ids, table, nseq, T):
         """ids int32 [nseq*T] -> pooled LayerNorm'd mean [nseq, D]."""
-        D, H, dev = self.D, self.H, self.dev
+        D, dev = self.D, self.dev
         M = nseq * T
         x = torch.empty(M, D, dtype=torch.float32, device=dev)
         lib.embed(ids, None, M, D, table, None, x)
-        a = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
-        qkv = torch.empty(M, 3 * D, dtype=torch.bfloat16, device=dev)
-        o = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
-        h = torch.empty(M, 2 * D, dtype=torch.bfloat16, device=dev)
-        for lw in enc.layers:
-            lib.rmsnorm(x, M, D, lw["g_attn"], a)
-            lib.gemm(a, lw["wqkv"], M=M, N=3 * D, K=D, out_bf16=qkv)
-            lib.clvp_rotary(qkv, nseq, T, H)
-            lib.attention(qkv, o, nseq=nseq, T=T, H=H, ld=3 * D, ldo=D, k_off=D, v_off=2 * D, scale=0.125)
-            lib.gemm(o, lw["wout"], M=M, N=D, K=D, bias=lw["bout"], residual=x, out_f32=x)
-            lib.rmsnorm(x, M, D, lw["g_ff"], a)
-            lib.gemm(a, lw["w1"], M=M, N=4 * D, K=D, bias=lw["b1"], act=lib.ACT_GEGLU, out_bf16=h)
-            lib.gemm(h, lw["w2"], M=M, N=D, K=2 * D, bias=lw["b2"], residual=x, out_f32=x)
+        encoder_layers(enc, x, nseq, T, D, self.H, dev)
         pooled = torch.empty(nseq, D, dtype=torch.float32, device=dev)
         lib.clvp_pool(x, nseq, T, D, enc.norm_g, enc.norm_b, pooled)
         return pooled

@@ -37,6 +37,10 @@ class ModelConfig:
     clvp_heads: int = 12
     clvp_text_tokens: int = 256
     clvp_speech_tokens: int = 8192
+    # CVVP (api.py:252-256; only used when tts(cvvp_amount > 0, voice_samples=...))
+    cvvp_dim: int = 512
+    cvvp_depth: int = 8
+    cvvp_heads: int = 8
     # UnivNet (vocoder.py:232-233)
     voc_noise_dim: int = 64
     voc_channels: int = 32
@@ -62,12 +66,12 @@ class ModelConfig:
     def small():
         return ModelConfig(ar_layers=2, ar_dim=128, ar_heads=2, cond_enc_blocks=1,
                            diff_dim=128, diff_layers=2, diff_heads=2,
-                           clvp_dim=128, clvp_depth=2, clvp_heads=2)
+                           clvp_dim=128, clvp_depth=2, clvp_heads=2, cvvp_dim=128, cvvp_depth=2, cvvp_heads=2)
 
     @staticmethod
     def medium():
         """Full widths, few layers: exercises every full-size tile shape cheaply."""
-        return ModelConfig(ar_layers=2, cond_enc_blocks=1, diff_layers=1, clvp_depth=2)
+        return ModelConfig(ar_layers=2, cond_enc_blocks=1, diff_layers=1, clvp_depth=2, cvvp_depth=2)
 
 
 VOC_STRIDES = (8, 8, 4)          # vocoder.py:232

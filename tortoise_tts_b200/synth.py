@@ -185,6 +185,47 @@ def synth_clvp(cfg: ModelConfig, seed=0):
     return sd
 
 
+def synth_cvvp(cfg: ModelConfig, seed=0):
+    """`cvvp.pth` (CVVP.state_dict() as api.py:254-255 builds it: mel_codes=8192, depths 8, latent_multiplier 1;
+    cvvp.py:64-106). The transformers are plain ContinuousTransformerWrappers: no `.wrap.` in the layer keys."""
+    g = _Gen(seed * 1000 + 6)
+    D = cfg.cvvp_dim
+    sd = {}
+    sd["temperature"] = torch.tensor(1.0)
+    sd["cond_emb.0.weight"] = g.lin((D // 2, 80, 5), 80 * 5)
+    sd["cond_emb.0.bias"] = g.bias(D // 2)
+    sd["cond_emb.1.weight"] = g.lin((D, D // 2, 3), (D // 2) * 3)
+    sd["cond_emb.1.bias"] = g.bias(D)
+    sd["to_conditioning_latent.weight"] = g.lin((D, D), D)
+    sd["speech_emb.emb.weight"] = g.normal((cfg.clvp_speech_tokens, D), 1.0)
+    sd["to_speech_latent.weight"] = g.lin((D, D), D)
+    for enc in ("conditioning", "speech"):
+        p = f"{enc}_transformer.transformer."
+        for l in range(cfg.cvvp_depth):
+            a = f"{p}attn_layers.layers.{2 * l}."
+            sd[a + "0.0.g"] = g.gamma(D)
+            for nm in ("to_q", "to_k", "to_v"):
+                sd[a + f"1.{nm}.weight"] = g.lin((D, D), D)
+            sd[a + "1.to_out.weight"] = g.lin((D, D), D, 0.5)
+            sd[a + "1.to_out.bias"] = g.bias(D)
+            f = f"{p}attn_layers.layers.{2 * l + 1}."
+            sd[f + "0.0.g"] = g.gamma(D)
+            sd[f + "1.net.0.proj.weight"] = g.lin((2 * D, D), D)          # ff_mult = 1, GLU: 2 x inner rows
+            sd[f + "1.net.0.proj.bias"] = g.bias(2 * D)
+            sd[f + "1.net.3.weight"] = g.lin((D, D), D, 0.5)
+            sd[f + "1.net.3.bias"] = g.bias(D)
+        sd[p + "attn_layers.rotary_pos_emb.inv_freq"] = 1.0 / (10000 ** (torch.arange(0, 32, 2).float() / 32))
+        sd[p + "norm.weight"] = g.gamma(D)
+        sd[p + "norm.bias"] = g.beta(D)
+        c = f"{enc}_transformer.pre_combiner."
+        sd[c + "0.weight"] = g.lin((D, D, 1), D)
+        sd[c + "0.bias"] = g.bias(D)
+        _attention_block(sd, g, c + "1.", D, cfg.cvvp_heads, rel_pos=False)
+        sd[c + "2.weight"] = g.lin((D, D, 1), D)
+        sd[c + "2.bias"] = g.bias(D)
+    return sd
+
+
 def _wn(sd, g, prefix, shape, fan_in, gain=1.0):
     """weight-norm pair (weight_g over all dims but 0, vocoder.py:290-298)."""
     v = g.lin(shape, fan_in, gain)
@@ -238,6 +279,7 @@ def synth_all(cfg: ModelConfig, seed=0, suppress_stop=True):
         "vocoder": synth_vocoder(cfg, seed),
         "rlg_auto": synth_rlg(cfg.ar_dim, seed),
         "rlg_diffuser": synth_rlg(2 * cfg.diff_dim, seed + 1),
+        "cvvp": synth_cvvp(cfg, seed),
     }
 
 
@@ -251,4 +293,5 @@ def write_models_dir(path, cfg: ModelConfig, seed=0, suppress_stop=True):
     torch.save({"model_g": sds["vocoder"]}, os.path.join(path, "vocoder.pth"))
     torch.save(synth_rlg(cfg.ar_dim, seed), os.path.join(path, "rlg_auto.pth"))
     torch.save(synth_rlg(2 * cfg.diff_dim, seed), os.path.join(path, "rlg_diffuser.pth"))
+    torch.save(sds["cvvp"], os.path.join(path, "cvvp.pth"))
     return sds
