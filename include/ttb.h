@@ -24,7 +24,7 @@ int ttb_version(void);
 int ttb_device_ok(void);
 
 /* ---------------------------------------------------------------- dense contraction (tcgen05) */
-enum { TTB_ACT_NONE = 0, TTB_ACT_GELU_NEW = 1, TTB_ACT_SILU = 2, TTB_ACT_GEGLU = 3, TTB_ACT_LRELU02 = 4 };
+enum { TTB_ACT_NONE = 0, TTB_ACT_GELU_NEW = 1, TTB_ACT_SILU = 2, TTB_ACT_GEGLU = 3, TTB_ACT_LRELU02 = 4, TTB_ACT_TANH = 5 };
 
 typedef struct TtbGemmArgs {
   const void* A;        /* bf16 [batch, rows, lda] activations (K contiguous) */
@@ -56,6 +56,8 @@ typedef struct TtbGemmArgs {
                            block, i.e. one partial per (batch item, group, row block) for 32 channels per group. Needs
                            N == 32 * gn_groups and ceil(M / 32) <= TTB_GROUPNORM_SPLITS; consumed by ttb_groupnorm_apply. */
   int gn_groups;
+  int tap_dilation;     /* > 1: conv taps are tap_dilation rows apart (dilated Conv1d; `pad` stays in rows, e.g.
+                           dilation * (k - 1) / 2); 0 / 1 = adjacent rows */
 } TtbGemmArgs;
 
 /* nn.Linear / HF Conv1D / nn.Conv1d(k=1,3) as one tcgen05 GEMM with fused bias/activation/residual.
@@ -248,6 +250,17 @@ int ttb_peer_alloc(long long bytes, void** ptr, void* handle64);
 int ttb_peer_open(const void* handle64, void** ptr);
 int ttb_peer_close(void* ptr);
 int ttb_peer_free(void* ptr);
+/* ---------------------------------------------------------------- HiFiGAN decoder of the api_fast path (token-major) */
+/* v = leaky_relu((a + b + c) * scale, slope) for fp32 [R, C] inputs (b, c may be NULL; slope 1 = identity) written as the
+ * error-compensated bf16 triple [hi | lo | hi] (3C columns, zero-filled up to ldo) that a GEMM contracts with weights
+ * packed [Wh | Wh | Wl]: fp32-grade products from bf16 tensor-core operands (as ttb_voc_to_tokens_bf16 split != 0).
+ * Serves F.leaky_relu before every HiFiGAN convolution and the mean over the three ResBlocks
+ * (hifigan_decoder.py:92-95,254-265). */
+int ttb_act_split_cast(const float* a, const float* b, const float* c, float scale, float slope, int R, int C, void* out,
+                       int ldo, void* stream);
+/* F.interpolate(mode='linear', align_corners=False, scale_factor=1/rscale) along tokens: x fp32 [N, C] -> [S, C]
+ * (hifigan_decoder.py:283-292). src = (s + 0.5) * rscale - 0.5 clamped at 0, neighbours clamped at N - 1. */
+int ttb_interp_linear(const float* x, int N, int C, float rscale, int S, float* out, void* stream);
 /* misc small device helpers */
 int ttb_counter_add(int* counter, int delta, void* stream);
 int ttb_transpose_f32(const float* in, int R, int Cc, float* out, void* stream);           /* [R, C] -> [C, R] */

@@ -44,4 +44,12 @@ def build_reference_models(cfg, sds, kv_cache=True):
                 conditioning_enc_depth=cfg.cvvp_depth, cond_mask_percentage=0, speech_enc_depth=cfg.cvvp_depth,
                 speech_mask_percentage=0, latent_multiplier=1).eval()          # api.py:254-255
     cvvp.load_state_dict(sds["cvvp"], strict=True)
-    return {"autoregressive": ar, "diffusion": diff, "clvp": clvp, "vocoder": voc, "cvvp": cvvp, "missing": missing}
+    from tortoise.models.hifigan_decoder import HifiganGenerator
+    hifi = HifiganGenerator(in_channels=cfg.ar_dim, out_channels=1, resblock_type="1",
+                            resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]], resblock_kernel_sizes=[3, 7, 11],
+                            upsample_kernel_sizes=[16, 16, 4, 4], upsample_initial_channel=cfg.hifi_channels,
+                            upsample_factors=[8, 8, 2, 2], cond_channels=cfg.ar_dim).eval()      # api_fast.py:221-224
+    hifi.device = torch.device("cpu")
+    hifi.load_state_dict(sds["hifigan"], strict=True)
+    return {"autoregressive": ar, "diffusion": diff, "clvp": clvp, "vocoder": voc, "cvvp": cvvp, "hifigan": hifi,
+            "missing": missing}

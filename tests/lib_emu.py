@@ -7,7 +7,7 @@ import math
 import torch
 import torch.nn.functional as F
 
-ACT_NONE, ACT_GELU_NEW, ACT_SILU, ACT_GEGLU, ACT_LRELU02 = 0, 1, 2, 3, 4
+ACT_NONE, ACT_GELU_NEW, ACT_SILU, ACT_GEGLU, ACT_LRELU02, ACT_TANH = 0, 1, 2, 3, 4, 5
 
 
 def _v(t, sizes, strides):
@@ -16,7 +16,7 @@ def _v(t, sizes, strides):
 
 def gemm(A, W, *, M, N, K, bias=None, residual=None, out_f32=None, out_bf16=None, lda=None, rows=None, batch=1,
          a_bstride=0, res_bstride=0, outf_bstride=0, outb_bstride=0, ldr=None, ldo=None, ldob=None, taps=1, pad=0,
-         act=ACT_NONE, alpha=1.0, tile_n=0, force_ref=False, splitk=1, cluster=0, variant=0, gn_partials=None, gn_groups=0):
+         act=ACT_NONE, alpha=1.0, tile_n=0, force_ref=False, splitk=1, cluster=0, variant=0, gn_partials=None, gn_groups=0, tap_dilation=1):
     n_out = N // 2 if act == ACT_GEGLU else N
     lda = K if lda is None else lda
     rows = M if rows is None else rows
@@ -27,7 +27,7 @@ def gemm(A, W, *, M, N, K, bias=None, residual=None, out_f32=None, out_bf16=None
     w = W.float().reshape(N, taps, K)
     acc = torch.zeros(batch, M, N)
     for tap in range(taps):
-        sh = tap - pad
+        sh = tap * max(tap_dilation, 1) - pad
         lo, hi = max(0, -sh), min(M, rows - sh)
         if hi > lo:
             acc[:, lo:hi] += a[:, lo + sh:hi + sh] @ w[:, tap].t()
@@ -42,6 +42,8 @@ def gemm(A, W, *, M, N, K, bias=None, residual=None, out_f32=None, out_bf16=None
         acc = F.silu(acc)
     elif act == ACT_LRELU02:
         acc = F.leaky_relu(acc, 0.2)
+    elif act == ACT_TANH:
+        acc = torch.tanh(acc)
     if residual is not None and act != ACT_GEGLU:
         acc = acc + _v(residual, (batch, M, n_out), (res_bstride, ldr, 1))
     if splitk > 1:   # raw partials: the whole sum in split 0, zeros elsewhere (only the sum is observable)
@@ -451,6 +453,29 @@ def audio_stft_mel(x, n, n_fft, hop, window, twiddle, fb, n_mels, power, clip, f
         o = _v(out_bf16, (frames, ldo), (ldo, 1))
         o.zero_()
         o[:, :n_mels] = y.to(torch.bfloat16)
+
+
+def act_split_cast(a, R, Cc, out, ldo, b=None, c=None, scale=1.0, slope=1.0):
+    v = _v(a, (R, Cc), (Cc, 1)).clone()
+    for t in (b, c):
+        if t is not None:
+            v = v + _v(t, (R, Cc), (Cc, 1))
+    v = v * scale
+    v = torch.where(v > 0, v, v * slope)
+    hi = v.to(torch.bfloat16)
+    lo = (v - hi.float()).to(torch.bfloat16)
+    o = _v(out, (R, ldo), (ldo, 1))
+    o.zero_()
+    o[:, :Cc], o[:, Cc:2 * Cc], o[:, 2 * Cc:3 * Cc] = hi, lo, hi
+
+
+def interp_linear(x, N, Cc, rscale, S, out):
+    src = ((torch.arange(S, dtype=torch.float32) + 0.5) * rscale - 0.5).clamp(min=0)
+    i0 = src.floor().long().clamp(max=N - 1)
+    i1 = (i0 + 1).clamp(max=N - 1)
+    l1 = (src - i0.float()).unsqueeze(1)
+    xx = _v(x, (N, Cc), (Cc, 1))
+    _v(out, (S, Cc), (Cc, 1)).copy_(xx[i0] * (1 - l1) + xx[i1] * l1)
 
 
 def mean_rows(x, R, Cc, ld, scale, out, accumulate=False):

@@ -101,6 +101,48 @@ def test_gemm_groupnorm_statistics_in_epilogue(S, taps, residual, kw):
     assert (got - two).abs().max().item() < 1e-3
 
 
+@pytest.mark.parametrize("T,C,N,k,dil", [(1000, 64, 64, 3, 3), (517, 256, 256, 11, 5), (2000, 32, 32, 7, 1), (300, 128, 1, 7, 1)])
+def test_gemm_dilated_taps_split_operands(T, C, N, k, dil):
+    """Dilated Conv1d as ONE GEMM (TtbGemmArgs.tap_dilation) on error-compensated operands (ttb_act_split_cast triple
+    [hi | lo | hi] x [Wh | Wh | Wl]) with leaky_relu on the input and tanh on the output, against F.conv1d in fp32
+    (hifigan_decoder.py:92-95: xt = conv(leaky_relu(x)))."""
+    from tortoise_tts_b200 import lib
+    from tortoise_tts_b200.hifigan_engine import _kt, _pack_conv
+    torch.manual_seed(13)
+    x = torch.randn(T, C, device="cuda")
+    w = torch.randn(N, C, k) * (1.0 / (C * k) ** 0.5)
+    b = torch.randn(N, device="cuda") * 0.1
+    a = torch.empty(T, _kt(C), dtype=torch.bfloat16, device="cuda")
+    lib.act_split_cast(x, T, C, a, _kt(C), slope=0.1)
+    out = torch.empty(T, N, device="cuda")
+    lib.gemm(a, _pack_conv(w, "cuda"), M=T, N=N, K=_kt(C), taps=k, pad=dil * (k - 1) // 2, tap_dilation=dil, bias=b,
+             out_f32=out, act=lib.ACT_TANH, tile_n=32 if N <= 32 else 0)
+    want = torch.tanh(F.conv1d(F.leaky_relu(x, 0.1).t().unsqueeze(0), w.cuda(), b, dilation=dil,
+                               padding=dil * (k - 1) // 2))[0].t()
+    err = (out - want).abs().max().item()
+    report("dilated conv GEMM, split operands T=%d C=%d N=%d k=%d d=%d" % (T, C, N, k, dil), err)
+    assert err < 2e-4
+
+
+def test_interp_linear():
+    """F.interpolate(mode='linear') with an explicit scale factor, twice, as HifiganGenerator.inference does."""
+    from tortoise_tts_b200 import lib
+    torch.manual_seed(14)
+    L, C = 57, 64
+    x = torch.randn(L, C, device="cuda")
+    T1 = int(L * 4.0)
+    T = int(T1 * (24000 / 22050))
+    u1 = torch.empty(T1, C, device="cuda")
+    lib.interp_linear(x, L, C, 0.25, T1, u1)
+    u2 = torch.empty(T, C, device="cuda")
+    lib.interp_linear(u1, T1, C, 22050.0 / 24000.0, T, u2)
+    w1 = F.interpolate(x.t().unsqueeze(0), scale_factor=[4.0], mode="linear")
+    w2 = F.interpolate(w1, scale_factor=[24000 / 22050], mode="linear")
+    assert w2.shape[-1] == T
+    assert (u1 - w1[0].t()).abs().max().item() < 1e-5
+    assert (u2 - w2[0].t()).abs().max().item() < 1e-5
+
+
 @pytest.mark.parametrize("T,H,nseq,causal,use_bias", [(45, 2, 2, False, True), (174, 16, 1, True, False),
                                                       (374, 16, 2, False, True), (130, 12, 3, False, False),
                                                       (64, 2, 1, False, False), (128, 2, 2, True, True),

@@ -366,6 +366,31 @@ def test_tts_end_to_end_small(small):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("which,L", [("small", 23), ("full", 60)])
+def test_hifigan_engine(which, L):
+    """HifiganGenerator.inference (hifigan_decoder.py:270-294) at the api_fast configuration (512 initial
+    channels, x 8 8 2 2, ResBlock1 k 3/7/11) against oracle/hifigan.py run on the GPU in fp32."""
+    from tortoise_tts_b200.config import ModelConfig
+    from tortoise_tts_b200.synth import synth_hifigan
+    from tortoise_tts_b200.hifigan_engine import HifiganEngine
+    from oracle import hifigan as oh
+    cfg = ModelConfig.small() if which == "small" else ModelConfig.full()
+    sd = synth_hifigan(cfg, 0)
+    torch.manual_seed(22)
+    lat = torch.randn(L, cfg.ar_dim)
+    spk = torch.randn(cfg.ar_dim)
+    eng = HifiganEngine(sd, cfg)
+    got = eng.inference(lat, spk).cpu()
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad(), torch.device("cuda"):
+        want = oh.inference(sdc, lat.cuda().unsqueeze(0), spk.cuda().unsqueeze(0))[0, 0].cpu()
+    assert got.shape == want.shape == (256 * eng.output_frames(L),)
+    e = (got - want).abs().max().item()
+    report("HiFiGAN waveform %s L=%d abs (range +-1, peak %.2f)" % (which, L, want.abs().max().item()), e)
+    assert e < 0.03 and want.abs().max().item() > 0.05
+
+
+@pytest.mark.gpu
 def test_tts_cvvp_amount_blend(small):
     """tts(voice_samples=..., cvvp_amount=a) ranks by cvvp * a + clvp * (1 - a) (api.py:450-472): the scores the facade
     ranked with against the oracle's CLVP and CVVP on the same codes and the same conditioning mels; a = 1 uses CVVP alone;

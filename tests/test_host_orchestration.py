@@ -131,6 +131,23 @@ def test_cvvp_engine(env):
         eng.scores(auto_conds, torch.full((1, 4), 8192))
 
 
+def test_hifigan_engine(env):
+    """HiFiGAN decoder of the api_fast path: interpolation lengths, weight-norm folding, the
+    ConvTranspose -> 3-tap GEMM rewrite, dilated taps, split operands, ResBlock streams -- against oracle/hifigan.py."""
+    from tortoise_tts_b200.hifigan_engine import HifiganEngine
+    from oracle import hifigan as oh
+    cfg, sds, g = env
+    torch.manual_seed(12)
+    lat = torch.randn(11, cfg.ar_dim)
+    spk = torch.randn(cfg.ar_dim)
+    eng = HifiganEngine(sds["hifigan"], cfg, device="cpu")
+    with torch.no_grad():
+        want = oh.inference(sds["hifigan"], lat.unsqueeze(0), spk.unsqueeze(0))[0, 0]
+    got = eng.inference(lat, spk)
+    assert got.shape == want.shape == (256 * eng.output_frames(11),)
+    assert (got - want).abs().max().item() < 2e-3, (got - want).abs().max().item()
+
+
 def test_vocoder_engine(env):
     from tortoise_tts_b200.vocoder_engine import VocoderEngine
     cfg, sds, g = env

@@ -169,6 +169,22 @@ def test_cvvp_scores(small):
     assert (got - want).abs().max().item() < 1e-5
 
 
+def test_hifigan(small):
+    """oracle/hifigan.py == HifiganGenerator.inference(gpt_latents, g=speaker latent) of the api_fast path
+    (hifigan_decoder.py:270-294); strict=True load of the synthetic hifidecoder.pth checks the key layout."""
+    from oracle import hifigan as oh
+    cfg, sds, m = small
+    torch.manual_seed(16)
+    lat = torch.randn(1, 9, cfg.ar_dim)
+    spk = torch.randn(1, cfg.ar_dim)
+    with torch.no_grad():
+        want = m["hifigan"].inference(lat, spk)
+        got = oh.inference(sds["hifigan"], lat, spk)
+    assert got.shape == want.shape and got.shape[-1] == 256 * int(int(9 * 4) * 24000 / 22050)
+    assert (got - want).abs().max().item() < 1e-5
+    assert want.abs().max().item() > 0.05          # a meaningful waveform, not a saturated / vanishing one
+
+
 def test_diffusion_forward_and_loop(small):
     from oracle import diffusion as od
     from tortoise.api import load_discrete_vocoder_diffuser, do_spectrogram_diffusion

@@ -41,6 +41,8 @@ class ModelConfig:
     cvvp_dim: int = 512
     cvvp_depth: int = 8
     cvvp_heads: int = 8
+    # HifiganGenerator of the `api_fast` path (api_fast.py:221-224): in_channels = ar_dim, cond_channels = ar_dim
+    hifi_channels: int = 512
     # UnivNet (vocoder.py:232-233)
     voc_noise_dim: int = 64
     voc_channels: int = 32
@@ -66,7 +68,7 @@ class ModelConfig:
     def small():
         return ModelConfig(ar_layers=2, ar_dim=128, ar_heads=2, cond_enc_blocks=1,
                            diff_dim=128, diff_layers=2, diff_heads=2,
-                           clvp_dim=128, clvp_depth=2, clvp_heads=2, cvvp_dim=128, cvvp_depth=2, cvvp_heads=2)
+                           clvp_dim=128, clvp_depth=2, clvp_heads=2, cvvp_dim=128, cvvp_depth=2, cvvp_heads=2, hifi_channels=128)
 
     @staticmethod
     def medium():
@@ -74,6 +76,10 @@ class ModelConfig:
         return ModelConfig(ar_layers=2, cond_enc_blocks=1, diff_layers=1, clvp_depth=2, cvvp_depth=2)
 
 
+HIFI_UP_FACTORS = (8, 8, 2, 2)   # api_fast.py:223 (kernel sizes 16, 16, 4, 4 = 2 x factor)
+HIFI_RES_KERNELS = (3, 7, 11)    # api_fast.py:222
+HIFI_RES_DILATIONS = (1, 3, 5)   # api_fast.py:222 (the same for the three kernel sizes)
+HIFI_LRELU = 0.1                 # hifigan_decoder.py:8
 VOC_STRIDES = (8, 8, 4)          # vocoder.py:232
 VOC_DILATIONS = (1, 3, 9, 27)    # vocoder.py:232
 VOC_LRELU = 0.2

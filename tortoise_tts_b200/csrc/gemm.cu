@@ -118,6 +118,7 @@ struct GemmEpilogue {
   int ldr, ldo, ldob;
   int act;                 // TTB_ACT_*
   float alpha;             // scales the accumulator before bias
+  int tap_dil;             // row distance between conv taps (dilation); 1 = plain
   float2* gn_part;         // GroupNorm partials [batch][groups][TTB_GN_SPLITS] of the output, or null (TtbGemmArgs.gn_partials)
   int gn_groups;
 };
@@ -193,10 +194,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         uint8_t* sb = sa + L::A_BYTES;
         if constexpr (SPLIT_PRODUCER) {
           mbar_arrive_expect_tx(&full_bar[stage], L::A_BYTES);
-          tma_load_3d(sa, &map_a, &full_bar[stage], kk, m0 + tap - pad, bz * a_batch_mul);
+          tma_load_3d(sa, &map_a, &full_bar[stage], kk, m0 + tap * ep.tap_dil - pad, bz * a_batch_mul);
         } else {
           mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          tma_load_3d(sa, &map_a, &full_bar[stage], kk, m0 + tap - pad, bz * a_batch_mul);
+          tma_load_3d(sa, &map_a, &full_bar[stage], kk, m0 + tap * ep.tap_dil - pad, bz * a_batch_mul);
           tma_load_3d(sb, &map_b, &full_bar[stage], tap * K + kk, n0, 0);
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -420,6 +421,11 @@ extern "C" int ttb_gemm(const TtbGemmArgs* gp, void* stream) {
   ep.res_bstride = g.res_bstride; ep.outf_bstride = g.outf_bstride; ep.outb_bstride = g.outb_bstride;
   ep.ldr = g.ldr; ep.ldo = g.ldo; ep.ldob = g.ldob; ep.act = g.act; ep.alpha = g.alpha;
   ep.gn_part = nullptr; ep.gn_groups = g.gn_groups;
+  ep.tap_dil = g.tap_dilation > 1 ? g.tap_dilation : 1;
+  if (ep.tap_dil > 1 && (g.cluster > 1 || g.variant == 6 || g.force_ref || g_gemm_impl == 1)) {
+    set_error("ttb_gemm: tap_dilation is implemented by the one-tile and the persistent kernels only");
+    return -1;
+  }
   if (g.gn_partials) {
     if (g.N != 32 * g.gn_groups || (g.M + 31) / 32 > TTB_GN_SPLITS || g.act == TTB_ACT_GEGLU || g.splitk > 1 || g.force_ref) {
       set_error("ttb_gemm: gn_partials needs N == 32 * gn_groups, M <= %d, no GEGLU / split-K (N=%d groups=%d M=%d)",

@@ -47,6 +47,7 @@ TTB_DEVINL float epi_act(float x) {
   if (ACT == TTB_ACT_GELU_NEW) return gelu_new(x);
   if (ACT == TTB_ACT_SILU) return silu(x);
   if (ACT == TTB_ACT_LRELU02) return leaky(x, 0.2f);
+  if (ACT == TTB_ACT_TANH) return tanhf(x);
   return x;
 }
 
@@ -234,6 +235,7 @@ TTB_DEVINL void gemm_epilogue_dispatch(uint32_t taddr, int n0, int N, int m_base
     case TTB_ACT_GELU_NEW: gemm_epilogue_tile<BN, TTB_ACT_GELU_NEW>(taddr, n0, N, m_base, M, lane, bz, ep, scratch, release_bar); break;
     case TTB_ACT_SILU: gemm_epilogue_tile<BN, TTB_ACT_SILU>(taddr, n0, N, m_base, M, lane, bz, ep, scratch, release_bar); break;
     case TTB_ACT_LRELU02: gemm_epilogue_tile<BN, TTB_ACT_LRELU02>(taddr, n0, N, m_base, M, lane, bz, ep, scratch, release_bar); break;
+    case TTB_ACT_TANH: gemm_epilogue_tile<BN, TTB_ACT_TANH>(taddr, n0, N, m_base, M, lane, bz, ep, scratch, release_bar); break;
     default: gemm_epilogue_tile<BN, TTB_ACT_NONE>(taddr, n0, N, m_base, M, lane, bz, ep, scratch, release_bar); break;
   }
 }

@@ -75,7 +75,7 @@ gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const 
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          tma_load_3d(sa, &map_a, &full_bar[stage], kk, m0 + tap - pad, bz * a_batch_mul);
+          tma_load_3d(sa, &map_a, &full_bar[stage], kk, m0 + tap * ep.tap_dil - pad, bz * a_batch_mul);
           tma_load_3d(sb, &map_b, &full_bar[stage], tap * K + kk, n0, 0);
           if (++stage == PSTAGES) { stage = 0; phase ^= 1; }
         }

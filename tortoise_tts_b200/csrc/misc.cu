@@ -341,6 +341,74 @@ extern "C" int ttb_enable_peer_access(int peer_device) {
   cudaGetLastError();
   return 0;
 }
+namespace ttb {
+__global__ void act_split_cast_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                                      float scale, float slope, int R, int C, __nv_bfloat16* __restrict__ out, int ldo) {
+  pdl_wait();
+  const int groups = ldo >> 2;                        // 4 output columns per thread
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)R * groups) return;
+  const int r = (int)(i / groups), g = (int)(i - (long long)r * groups);
+  const int col = g * 4;
+  uint32_t w0 = 0u, w1 = 0u;
+  if (col < 3 * C) {
+    const int part = col / C, cc = col - part * C;    // C % 4 == 0: a group never straddles two parts
+    const long long off = (long long)r * C + cc;
+    float4 v = *reinterpret_cast<const float4*>(a + off);
+    if (b) { const float4 t = *reinterpret_cast<const float4*>(b + off); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+    if (c) { const float4 t = *reinterpret_cast<const float4*>(c + off); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+    float x[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      x[k] = x[k] > 0.f ? x[k] : x[k] * slope;
+      if (part == 1) x[k] -= __bfloat162float(__float2bfloat16(x[k]));      // lo = v - bf16(v)
+    }
+    w0 = pack_bf16(x[0], x[1]);
+    w1 = pack_bf16(x[2], x[3]);
+  }
+  *reinterpret_cast<uint2*>(out + (long long)r * ldo + col) = make_uint2(w0, w1);
+}
+
+__global__ void interp_linear_kernel(const float* __restrict__ x, int N, int C, float rscale, int S, float* __restrict__ out) {
+  pdl_wait();
+  const int c4 = C >> 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)S * c4) return;
+  const int s = (int)(i / c4), c = (int)(i - (long long)s * c4) * 4;
+  // area_pixel_compute_source_index (align_corners = False, explicit scale): negative sources clamp to 0
+  float src = ((float)s + 0.5f) * rscale - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  int i0 = (int)src;
+  i0 = i0 > N - 1 ? N - 1 : i0;
+  const int i1 = i0 + (i0 < N - 1 ? 1 : 0);
+  const float l1 = src - (float)i0, l0 = 1.f - l1;
+  const float4 p = *reinterpret_cast<const float4*>(x + (long long)i0 * C + c);
+  const float4 q = *reinterpret_cast<const float4*>(x + (long long)i1 * C + c);
+  *reinterpret_cast<float4*>(out + (long long)s * C + c) = make_float4(l0 * p.x + l1 * q.x, l0 * p.y + l1 * q.y,
+                                                                         l0 * p.z + l1 * q.z, l0 * p.w + l1 * q.w);
+}
+}  // namespace ttb
+
+extern "C" int ttb_act_split_cast(const float* a, const float* b, const float* c, float scale, float slope, int R, int C,
+                                  void* out, int ldo, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((C & 3) || (ldo & 3) || ldo < 3 * C || R <= 0) { set_error("ttb_act_split_cast: C=%d ldo=%d unsupported", C, ldo); return -1; }
+  const long long n = (long long)R * (ldo >> 2);
+  launch_pdl(act_split_cast_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, st, a, b, c, scale, slope, R, C,
+             reinterpret_cast<__nv_bfloat16*>(out), ldo);
+  TTB_CHECK_LAUNCH("act_split_cast_kernel");
+  return 0;
+}
+
+extern "C" int ttb_interp_linear(const float* x, int N, int C, float rscale, int S, float* out, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((C & 3) || N <= 0 || S <= 0) { set_error("ttb_interp_linear: bad shape"); return -1; }
+  const long long n = (long long)S * (C >> 2);
+  launch_pdl(interp_linear_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, st, x, N, C, rscale, S, out);
+  TTB_CHECK_LAUNCH("interp_linear_kernel");
+  return 0;
+}
+
 extern "C" int ttb_counter_add(int* counter, int delta, void* stream) {
   counter_add_kernel<<<1, 1, 0, ST>>>(counter, delta);
   TTB_CHECK_LAUNCH("counter_add_kernel");

@@ -10,7 +10,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libttb.so")
 
-ACT_NONE, ACT_GELU_NEW, ACT_SILU, ACT_GEGLU, ACT_LRELU02 = 0, 1, 2, 3, 4
+ACT_NONE, ACT_GELU_NEW, ACT_SILU, ACT_GEGLU, ACT_LRELU02, ACT_TANH = 0, 1, 2, 3, 4, 5
 
 
 class TtbError(RuntimeError):
@@ -26,7 +26,7 @@ class GemmArgs(C.Structure):
                 ("rows", C.c_int), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
                 ("taps", C.c_int), ("pad", C.c_int), ("batch", C.c_int), ("act", C.c_int),
                 ("alpha", C.c_float), ("tile_n", C.c_int), ("force_ref", C.c_int), ("splitk", C.c_int), ("cluster", C.c_int), ("variant", C.c_int),
-                ("gn_partials", C.c_void_p), ("gn_groups", C.c_int)]
+                ("gn_partials", C.c_void_p), ("gn_groups", C.c_int), ("tap_dilation", C.c_int)]
 
 
 class AttnArgs(C.Structure):
@@ -67,7 +67,7 @@ _lib = None
 
 # every symbol include/ttb.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
-    "ttb_last_error", "ttb_version", "ttb_device_ok", "ttb_gemm", "ttb_layernorm", "ttb_rmsnorm", "ttb_groupnorm", "ttb_groupnorm_apply",
+    "ttb_last_error", "ttb_version", "ttb_device_ok", "ttb_gemm", "ttb_layernorm", "ttb_rmsnorm", "ttb_groupnorm", "ttb_groupnorm_apply", "ttb_act_split_cast", "ttb_interp_linear",
     "ttb_residual_layernorm", "ttb_attention", "ttb_ar_embed_step", "ttb_ar_decode_attention", "ttb_ar_store_prefix", "ttb_ar_sample",
     "ttb_ar_fix_codes", "ttb_embed", "ttb_clvp_rotary", "ttb_clvp_pool", "ttb_clvp_project",
     "ttb_timestep_embedding", "ttb_linear_small", "ttb_interp_nearest", "ttb_diffusion_step", "ttb_counter_add",
@@ -131,7 +131,7 @@ def _f32(t):
 # ------------------------------------------------------------------ wrappers
 def gemm(A, W, *, M, N, K, bias=None, residual=None, out_f32=None, out_bf16=None, lda=None, rows=None, batch=1,
          a_bstride=0, res_bstride=0, outf_bstride=0, outb_bstride=0, ldr=None, ldo=None, ldob=None, taps=1, pad=0,
-         act=ACT_NONE, alpha=1.0, tile_n=0, force_ref=False, splitk=1, cluster=0, variant=0, gn_partials=None, gn_groups=0):
+         act=ACT_NONE, alpha=1.0, tile_n=0, force_ref=False, splitk=1, cluster=0, variant=0, gn_partials=None, gn_groups=0, tap_dilation=1):
     """See include/ttb.h ttb_gemm. A: bf16 [batch, rows, lda]; W: bf16 [N, taps*K]. `gn_partials` (a groupnorm_scratch
     buffer): the epilogue also leaves the GroupNorm statistics of the output there (consumed by groupnorm_apply)."""
     _bf(A), _bf(W), _f32(bias), _f32(residual), _f32(out_f32), _bf(out_bf16)
@@ -149,6 +149,7 @@ def gemm(A, W, *, M, N, K, bias=None, residual=None, out_f32=None, out_bf16=None
     g.alpha, g.tile_n, g.force_ref, g.splitk, g.cluster = alpha, tile_n, 1 if force_ref else 0, splitk, cluster
     g.variant = variant
     g.gn_partials, g.gn_groups = _p(_f32(gn_partials)).value or 0, gn_groups
+    g.tap_dilation = tap_dilation
     _chk(load().ttb_gemm(C.byref(g), _stream()), "ttb_gemm")
 
 
@@ -389,6 +390,16 @@ def audio_stft_mel(x, n, n_fft, hop, window, twiddle, fb, n_mels, power, clip, f
     _chk(load().ttb_audio_stft_mel(_p(_f32(x)), n, n_fft, hop, _p(_f32(window)), _p(_f32(twiddle)), _p(_f32(fb)), n_mels,
                                    power, 1 if clip else 0, C.c_float(floor_v), _p(_f32(div)), _p(_bf(out_bf16)), ldo,
                                    _p(_f32(out_f32)), _stream()), "ttb_audio_stft_mel")
+
+
+def act_split_cast(a, R, Cc, out, ldo, b=None, c=None, scale=1.0, slope=1.0):
+    """out bf16 [R, ldo] = [hi | lo | hi | 0...] of leaky_relu((a + b + c) * scale, slope); see include/ttb.h."""
+    _chk(load().ttb_act_split_cast(_p(_f32(a)), _p(_f32(b)), _p(_f32(c)), C.c_float(scale), C.c_float(slope), R, Cc,
+                                   _p(_bf(out)), ldo, _stream()), "ttb_act_split_cast")
+
+
+def interp_linear(x, N, Cc, rscale, S, out):
+    _chk(load().ttb_interp_linear(_p(_f32(x)), N, Cc, C.c_float(rscale), S, _p(_f32(out)), _stream()), "ttb_interp_linear")
 
 
 def mean_rows(x, R, Cc, ld, scale, out, accumulate=False):

@@ -259,6 +259,38 @@ def synth_vocoder(cfg: ModelConfig, seed=0):
     return sd
 
 
+def synth_hifigan(cfg: ModelConfig, seed=0):
+    """`hifidecoder.pth` (HifiganGenerator.state_dict() as api_fast.py:221-227 builds it, weight norm in place:
+    hifigan_decoder.py:159-238)."""
+    from .config import HIFI_UP_FACTORS, HIFI_RES_KERNELS
+    g = _Gen(seed * 1000 + 7)
+    C0, Cin = cfg.hifi_channels, cfg.ar_dim
+    sd = {}
+
+    def wn(prefix, shape, fan_in, nbias, gain=1.0):
+        v = g.lin(shape, fan_in, gain)
+        norm = v.reshape(shape[0], -1).norm(dim=1).reshape(shape[0], *([1] * (len(shape) - 1)))
+        sd[prefix + "bias"] = g.bias(nbias)
+        sd[prefix + "weight_g"] = norm * (1.0 + g.normal(norm.shape, 0.05))
+        sd[prefix + "weight_v"] = v
+
+    wn("conv_pre.", (C0, Cin, 7), 7 * Cin, C0)
+    ch = C0
+    for i, u in enumerate(HIFI_UP_FACTORS):
+        # ConvTranspose1d weight [in, out, k]: every output sums in * 2 taps
+        wn(f"ups.{i}.", (ch, ch // 2, 2 * u), 2 * ch, ch // 2)
+        ch //= 2
+        for j, k in enumerate(HIFI_RES_KERNELS):
+            p = f"resblocks.{i * len(HIFI_RES_KERNELS) + j}."
+            for m in range(3):
+                wn(p + f"convs1.{m}.", (ch, ch, k), k * ch, ch)
+                wn(p + f"convs2.{m}.", (ch, ch, k), k * ch, ch, 0.5)
+    wn("conv_post.", (1, ch, 7), 7 * ch, 1, 3.0)
+    sd["cond_layer.weight"] = g.lin((C0, Cin, 1), Cin)
+    sd["cond_layer.bias"] = g.bias(C0)
+    return sd
+
+
 def synth_rlg(C, seed=0):
     """`rlg_auto.pth` / `rlg_diffuser.pth` (RandomLatentConverter, random_latent_generator.py:40-50)."""
     g = _Gen(seed * 1000 + 5 + C)
@@ -280,6 +312,7 @@ def synth_all(cfg: ModelConfig, seed=0, suppress_stop=True):
         "rlg_auto": synth_rlg(cfg.ar_dim, seed),
         "rlg_diffuser": synth_rlg(2 * cfg.diff_dim, seed + 1),
         "cvvp": synth_cvvp(cfg, seed),
+        "hifigan": synth_hifigan(cfg, seed),
     }
 
 
@@ -294,4 +327,5 @@ def write_models_dir(path, cfg: ModelConfig, seed=0, suppress_stop=True):
     torch.save(synth_rlg(cfg.ar_dim, seed), os.path.join(path, "rlg_auto.pth"))
     torch.save(synth_rlg(2 * cfg.diff_dim, seed), os.path.join(path, "rlg_diffuser.pth"))
     torch.save(sds["cvvp"], os.path.join(path, "cvvp.pth"))
+    torch.save(sds["hifigan"], os.path.join(path, "hifidecoder.pth"))
     return sds
