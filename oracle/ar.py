@@ -197,6 +197,21 @@ def latents(sd, cfg, cond_latent, text_tokens, codes):
     return enc[:, -(L + 2):][:, :-2]
 
 
+def stream_latents(sd, cfg, cond_latent, text_tokens, codes, pos_mode="ref_kv_quirk"):
+    """Latents the streaming generator of the api_fast path yields next to its tokens
+    (stream_generator.py:982: `final_norm(outputs.hidden_states[-1][:, -1])`, hidden_states[-1] = after ln_f, of the
+    forward that produced the logits token i was sampled from). codes [n] (LongTensor, the yielded tokens, stop token
+    included) -> [n, D]: row i belongs to the input [start, c_0 .. c_{i-1}] under the position rule of `pos_mode`."""
+    codes = codes.reshape(1, -1)
+    n = codes.shape[1]
+    prompt = prompt_embeddings(sd, cfg, cond_latent, text_tokens)
+    ids = torch.cat([torch.full((1, 1), cfg.start_mel_token, dtype=torch.long), codes[:, : n - 1]], dim=1)
+    pos = torch.tensor([mel_pos_index(j, pos_mode) for j in range(n)], dtype=torch.long)
+    me = sd["mel_embedding.weight"][ids] + sd["mel_pos_embedding.emb.weight"][pos]
+    hidden, _ = gpt2_trunk(sd, cfg, torch.cat([prompt, me], dim=1))
+    return _ln(hidden[0, prompt.shape[1]:], sd["final_norm.weight"], sd["final_norm.bias"])
+
+
 def calm_trim_length(codes_row, calm_token=83):
     """api.py:547-556: index at which latents are cut (first run of >8 calm tokens), or len."""
     c = 0

@@ -471,3 +471,73 @@ def test_tts_long_concatenates_chunks(small):
         tts.tts_long("a|b", preset="ultra_fast", text_tokens_list=toks, k=2, **kw)
     with pytest.raises(ValueError):
         tts.tts_long("a|b|c", preset="ultra_fast", text_tokens_list=toks, **kw)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["small", "medium"])
+def test_api_fast_tts_and_stream(which, small, medium):
+    """SURVEY 8f row 3 through the drop-in facade of `tortoise.api_fast.TextToSpeech`: `tts()` (one sequence decoded by the
+    one-kernel decode step at B = 1 -> UnifiedVoice latents of the raw codes -> HiFiGAN) and `tts_stream()` (block-wise
+    decode, stream latents, every flush decoding all latents so far, cross-faded chunks) against the oracle run on the
+    SAME codes (oracle/ar.py latents / stream_latents + oracle/hifigan.py, both pinned against the reference modules).
+    Tolerance: 0.05 on the +-1 waveform (bf16 GEMM operands in the 2-layer GPT trunk: latents within 3 %)."""
+    from tortoise_tts_b200 import api_fast
+    from oracle import ar as oar, hifigan as oh
+    cfg, sds = (small[0], small[1]) if which == "small" else medium
+    tts = api_fast.TextToSpeech(state_dicts=sds, config=cfg, kv_cache=True)
+    text = TEXT[:-1]
+    toks = text + [0]
+    voice = torch.randn(1, cfg.ar_dim, generator=torch.Generator().manual_seed(3))
+    tts.get_random_conditioning_latents = lambda: voice.cuda()
+    P = len(toks) + 4
+    old = api_fast.STREAM_MAX_LENGTH
+    api_fast.STREAM_MAX_LENGTH = P + 100
+    try:
+        chunks = [c.cpu() for c in tts.tts_stream("unused", text_tokens=text, use_deterministic_seed=11,
+                                                  stream_chunk_size=16, overlap_wav_len=512, verbose=False)]
+        again = [c.cpu() for c in tts.tts_stream("unused", text_tokens=text, use_deterministic_seed=11,
+                                                 stream_chunk_size=16, overlap_wav_len=512, verbose=False)]
+    finally:
+        api_fast.STREAM_MAX_LENGTH = old
+    assert len(chunks) == len(again) and all(torch.equal(a, b) for a, b in zip(chunks, again))
+    g = torch.Generator(device="cuda")
+    g.manual_seed(11)
+    u = torch.rand(1, 100, generator=g, device="cuda")
+    codes = tts.autoregressive.generate(voice.reshape(-1), toks, 1, 100, uniforms=u).cpu().long()[0]
+    hit = (codes == cfg.stop_mel_token).nonzero()
+    n = int(hit[0]) + 1 if hit.numel() else 100
+    sd_ar = {k: v.cuda().float() for k, v in sds["autoregressive"].items()}
+    sd_h = {k: v.cuda().float() for k, v in sds["hifigan"].items()}
+    want, buf, first, prev, tail = [], 0, 60, None, None
+    with torch.no_grad(), torch.device("cuda"):
+        for i in list(range(n)) + [None]:                      # api_fast.py:399-420, token by token
+            if i is not None:
+                buf += 1
+            if i is None or buf >= max(16, first):
+                first = 0
+                m = n if i is None else i + 1
+                lat = oar.stream_latents(sd_ar, cfg, voice.cuda(), toks, codes[:m].cuda(), "ref_kv_quirk")
+                wav = oh.inference(sd_h, lat.unsqueeze(0), voice.cuda())[0, 0]
+                c, prev, tail = tts.handle_chunks(wav, prev, tail, 512)
+                buf = 0
+                want.append(c.cpu())
+    assert len(chunks) == len(want)
+    e = max((a - b).abs().max().item() for a, b in zip(chunks, want))
+    assert all(a.shape == b.shape for a, b in zip(chunks, want))
+    report("api_fast tts_stream chunks %s (%d tokens, %d chunks) abs" % (which, n, len(want)), e)
+    assert e < 0.05
+    # ---- tts()
+    wav = tts.tts("unused", text_tokens=text, use_deterministic_seed=11, verbose=False)
+    nt = tts.last_timings["tokens"]
+    assert wav.dim() == 3 and wav.shape[:2] == (1, 1) and wav.dtype == torch.float32
+    g.manual_seed(11)
+    u = torch.rand(1, cfg.max_mel_tokens - 1, generator=g, device="cuda")
+    codes = tts.autoregressive.generate(voice.reshape(-1), toks, 1, cfg.max_mel_tokens - 1, uniforms=u).long()
+    assert nt <= cfg.max_mel_tokens - 1
+    with torch.no_grad(), torch.device("cuda"):
+        lat = oar.latents(sd_ar, cfg, voice.cuda(), toks, codes[:, :nt])
+        ref = oh.inference(sd_h, lat, voice.cuda())
+    assert wav.shape == ref.shape
+    e = (wav - ref).abs().max().item()
+    report("api_fast tts waveform %s (%d tokens) abs" % (which, nt), e)
+    assert e < 0.05

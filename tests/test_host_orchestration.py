@@ -52,6 +52,112 @@ def test_ar_engine(env):
     assert agree >= 13
 
 
+def test_ar_stream(env):
+    """Block-wise decoding of ONE sequence (the token stream of the api_fast path) == the batch decode loop, block
+    boundaries / end-of-stream handling, and the stream latents against the oracle (pinned against the reference's cached
+    forward in tests/test_oracle_vs_reference.py)."""
+    from tortoise_tts_b200.ar_engine import AREngine
+    from oracle import ar
+    cfg, sds, g = env
+    eng = AREngine(sds["autoregressive"], cfg, device="cpu")
+    text = g["text"].tolist()
+    torch.manual_seed(1)
+    u = torch.rand(1, 20)
+    full = eng.generate(g["ar_cond"], text, 1, 20, uniforms=u, use_graph=False)[0]
+    hit = (full == cfg.stop_mel_token).nonzero()
+    n_end = int(hit[0]) + 1 if hit.numel() else 20
+    out = list(eng.generate_stream(g["ar_cond"], text, 20, 6, 4, uniforms=u, use_graph=False))
+    want_bounds = [b for b in (6, 10, 14, 18) if b < n_end] + [n_end]
+    assert [int(c.numel()) for c, _ in out] == want_bounds
+    assert [e for _, e in out] == [False] * (len(out) - 1) + [True]
+    for c, _ in out:
+        assert torch.equal(c, full[: c.numel()])
+    codes = out[-1][0].long()
+    for mode in ("ref_kv_quirk",):
+        got = eng.stream_latents(g["ar_cond"], text, codes)
+        with torch.no_grad():
+            want = ar.stream_latents(sds["autoregressive"], cfg, g["ar_cond"], text, codes, pos_mode=mode)
+        assert got.shape == want.shape == (codes.numel(), cfg.ar_dim)
+        assert _rel(got, want) < 0.03
+
+
+def _fast_facade(cfg, sds):
+    """api_fast.TextToSpeech on the CPU emulation (the constructor insists on a CUDA device: fields set by hand)."""
+    from tortoise_tts_b200 import api_fast
+    from tortoise_tts_b200.ar_engine import AREngine
+    from tortoise_tts_b200.hifigan_engine import HifiganEngine
+    t = api_fast.TextToSpeech.__new__(api_fast.TextToSpeech)
+    t.cfg, t.device, t.kv_cache, t._sds = cfg, torch.device("cpu"), True, sds
+    t.autoregressive = AREngine(sds["autoregressive"], cfg, device="cpu")
+    t.hifi_decoder = HifiganEngine(sds["hifigan"], cfg, device="cpu")
+    t.rlg_auto = t._conditioning = t._tokenizer = None
+    t.models_dir = None
+    t.last_timings = {}
+    return t
+
+
+def test_api_fast_tts_and_stream(env, monkeypatch):
+    """Host logic of the api_fast facade on the emulated kernels: `tts` = one sequence -> latents of
+    the raw codes -> HiFiGAN; `tts_stream` = the reference's buffering rule (first max(chunk, first_buffer) tokens, then
+    every chunk, once more at the end), every flush decoding ALL latents so far, `handle_chunks` cutting and
+    cross-fading. Checked against a literal restatement of api_fast.py:396-420 driven by the oracle."""
+    from tortoise_tts_b200 import api_fast
+    from oracle import ar, hifigan as oh
+    cfg, sds, g = env
+    t = _fast_facade(cfg, sds)
+    text = g["text"].tolist()[:-1]              # the facade pads once itself
+    toks = text + [0]
+    P = len(toks) + 4
+    monkeypatch.setattr(api_fast, "STREAM_MAX_LENGTH", P + 30)
+    monkeypatch.setattr(api_fast, "FIRST_BUFFER", 12)
+    voice = torch.randn(1, cfg.ar_dim)
+    monkeypatch.setattr(t, "get_random_conditioning_latents", lambda: voice)
+    chunks = list(t.tts_stream("unused", text_tokens=text, use_deterministic_seed=3, stream_chunk_size=8,
+                               overlap_wav_len=256, verbose=False))
+    # the same tokens, from the engine (sampling parity is test_ar_engine's business)
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(3)
+    u = torch.rand(1, 30, generator=gen)
+    codes = t.autoregressive.generate(voice.reshape(-1), toks, 1, 30, uniforms=u, use_graph=False)[0].long()
+    hit = (codes == cfg.stop_mel_token).nonzero()
+    n = int(hit[0]) + 1 if hit.numel() else 30
+    want, buf, first, prev, tail = [], 0, 12, None, None
+    with torch.no_grad():
+        for i in list(range(n)) + [None]:        # None = StopIteration of the token generator
+            if i is not None:
+                buf += 1
+            if i is None or buf >= max(8, first):
+                first = 0
+                m = n if i is None else i + 1
+                lat = ar.stream_latents(sds["autoregressive"], cfg, voice, toks, codes[:m], "ref_kv_quirk")
+                wav = oh.inference(sds["hifigan"], lat.unsqueeze(0), voice)[0, 0]
+                c, prev, tail = t.handle_chunks(wav, prev, tail, 256)
+                buf = 0
+                want.append(c)
+    assert len(chunks) == len(want) and len(want) >= 3
+    for a, b in zip(chunks, want):
+        assert a.shape == b.shape
+        assert (a - b).abs().max().item() < 0.05, (a - b).abs().max().item()   # bf16 GEMM operands in the GPT trunk
+    # the pieces join into (almost) the whole utterance: everything but a cross-fade tail that is never handed out
+    assert sum(c.numel() for c in chunks) >= want[-1].numel()
+    # ---- tts(): raw codes incl. the stop token -> UnifiedVoice latents -> decoder
+    monkeypatch.setattr(type(cfg), "max_mel_tokens", property(lambda self: 25), raising=False)
+    try:
+        wav = t.tts("unused", text_tokens=text, use_deterministic_seed=3, verbose=False)
+    finally:
+        monkeypatch.undo()
+    nt = t.last_timings["tokens"]
+    gen.manual_seed(3)
+    u = torch.rand(1, 24, generator=gen)
+    codes = t.autoregressive.generate(voice.reshape(-1), toks, 1, 24, uniforms=u, use_graph=False).long()
+    assert nt == (int((codes[0] == cfg.stop_mel_token).nonzero()[0]) + 1 if (codes[0] == cfg.stop_mel_token).any() else 24)
+    with torch.no_grad():
+        lat = ar.latents(sds["autoregressive"], cfg, voice, toks, codes[:, :nt])
+        ref = oh.inference(sds["hifigan"], lat, voice)
+    assert wav.shape == ref.shape
+    assert (wav - ref).abs().max().item() < 0.05
+
+
 def test_clvp_engine(env):
     from tortoise_tts_b200.clvp_engine import CLVPEngine
     cfg, sds, g = env

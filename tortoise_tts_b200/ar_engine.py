@@ -236,18 +236,11 @@ class AREngine:
                       st["finished"], st["state"], sp["temperature"], sp["top_k"], sp["top_p"], sp["rep_penalty"],
                       self.cfg.stop_mel_token, advance=True)
 
-    def generate(self, cond_latent, text_tokens, num_candidates, max_new, uniforms=None, seed=None, temperature=0.8,
-                 top_k=50, top_p=0.8, repetition_penalty=2.0, pos_mode="ref_kv_quirk", use_graph=True,
-                 stop_check_every=32, trace_logits=None):
-        """≙ num_candidates/bs calls of UnifiedVoice.inference_speech (autoregressive.py:535-563), all candidates in
-        ONE batch with a shared-prefix KV cache. Returns int32 codes [num_candidates, max_new] padded with the
-        stop token (api.py:425-426). `uniforms` [B, max_new] injects the sampling randomness (parity mode)."""
+    def _begin(self, cond_latent, text_tokens, B, Nmax, uniforms, seed, sp, trace_logits=None):
+        """Workspace reset + prompt prefill + the first sampled token of every candidate."""
         cfg, dev = self.cfg, self.dev
-        B, Nmax = int(num_candidates), int(max_new)
         P = len(text_tokens) + 4  # cond + [start, tokens(padded), stop] + start_mel
         st = self._decode_state(B, P, Nmax)
-        sp = dict(temperature=float(temperature), top_k=int(top_k), top_p=float(top_p),
-                  rep_penalty=float(repetition_penalty), pos_mode=1 if pos_mode == "ref_kv_quirk" else 0)
         if uniforms is None:
             g = torch.Generator(device=dev)
             g.manual_seed(0 if seed is None else int(seed))
@@ -264,34 +257,61 @@ class AREngine:
         st["seen"][:, w] |= (1 << bit) if bit < 31 else -(1 << 31)
         self._prefill(cond_latent, text_tokens, st)
         if trace_logits is not None:   # parity hook (eager mode): logits the sampler sees at every step
-            use_graph = False
             trace_logits.append(st["logits"][:1].expand(B, -1).clone())
         lib.ar_sample(st["logits"], 0, self.V, B, st["uniforms"], Nmax, st["seen"], st["codes"], Nmax, st["finished"],
                       st["state"], sp["temperature"], sp["top_k"], sp["top_p"], sp["rep_penalty"], cfg.stop_mel_token,
                       advance=True)
+        return st
+
+    def _ensure_graph(self, st, sp):
+        """The decode step of this workspace as a CUDA graph (captured once per workspace + sampling parameters)."""
+        if st["graph"] is not None and st["graph_params"] == sp:
+            return
+        # warm-up once eagerly (module loading / attribute setting must not happen under capture),
+        # then restore the sampler state and capture
+        snap = {k: st[k].clone() for k in ("state", "codes", "seen", "finished")}
+        self._decode_step(st, sp)
+        torch.cuda.synchronize()
+        for k, v in snap.items():
+            st[k].copy_(v)
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        c0 = lib.CALLS
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                self._decode_step(st, sp)
+        st["graph_calls"] = lib.CALLS - c0
+        torch.cuda.current_stream().wait_stream(side)
+        for k, v in snap.items():
+            st[k].copy_(v)
+        st["graph"], st["graph_params"] = g, dict(sp)
+
+    def _check_step_flag(self, st):
+        flag = int(st["state"][2].item())      # TtbArState.reserved[0]: set by a timed-out wait inside the step kernel
+        if flag:
+            raise lib.TtbError("ar_step_kernel: internal wait timed out (code %d); results are invalid" % flag)
+
+    @staticmethod
+    def _sampling(temperature, top_k, top_p, repetition_penalty, pos_mode):
+        return dict(temperature=float(temperature), top_k=int(top_k), top_p=float(top_p),
+                    rep_penalty=float(repetition_penalty), pos_mode=1 if pos_mode == "ref_kv_quirk" else 0)
+
+    def generate(self, cond_latent, text_tokens, num_candidates, max_new, uniforms=None, seed=None, temperature=0.8,
+                 top_k=50, top_p=0.8, repetition_penalty=2.0, pos_mode="ref_kv_quirk", use_graph=True,
+                 stop_check_every=32, trace_logits=None):
+        """≙ num_candidates/bs calls of UnifiedVoice.inference_speech (autoregressive.py:535-563), all candidates in
+        ONE batch with a shared-prefix KV cache. Returns int32 codes [num_candidates, max_new] padded with the
+        stop token (api.py:425-426). `uniforms` [B, max_new] injects the sampling randomness (parity mode)."""
+        B, Nmax = int(num_candidates), int(max_new)
+        sp = self._sampling(temperature, top_k, top_p, repetition_penalty, pos_mode)
+        if trace_logits is not None:
+            use_graph = False
+        st = self._begin(cond_latent, text_tokens, B, Nmax, uniforms, seed, sp, trace_logits)
         steps = Nmax - 1
         if steps > 0:
             if use_graph:
-                if st["graph"] is None or st["graph_params"] != sp:
-                    # warm-up once eagerly (module loading / attribute setting must not happen under capture),
-                    # then restore the sampler state and capture
-                    snap = {k: st[k].clone() for k in ("state", "codes", "seen", "finished")}
-                    self._decode_step(st, sp)
-                    torch.cuda.synchronize()
-                    for k, v in snap.items():
-                        st[k].copy_(v)
-                    g = torch.cuda.CUDAGraph()
-                    side = torch.cuda.Stream()
-                    side.wait_stream(torch.cuda.current_stream())
-                    c0 = lib.CALLS
-                    with torch.cuda.stream(side):
-                        with torch.cuda.graph(g, stream=side):
-                            self._decode_step(st, sp)
-                    st["graph_calls"] = lib.CALLS - c0
-                    torch.cuda.current_stream().wait_stream(side)
-                    for k, v in snap.items():
-                        st[k].copy_(v)
-                    st["graph"], st["graph_params"] = g, dict(sp)
+                self._ensure_graph(st, sp)
                 done = 0
                 while done < steps:
                     n = min(stop_check_every, steps - done)
@@ -307,10 +327,48 @@ class AREngine:
                     if trace_logits is not None:
                         trace_logits.append(st["logits"].clone())
         if st["fused"] and steps > 0:
-            flag = int(st["state"][2].item())      # TtbArState.reserved[0]: set by a timed-out wait inside the step kernel
-            if flag:
-                raise lib.TtbError("ar_step_kernel: internal wait timed out (code %d); results are invalid" % flag)
+            self._check_step_flag(st)
         return st["codes"].clone()
+
+    def generate_stream(self, cond_latent, text_tokens, max_new, first_block, block, uniforms=None, seed=None,
+                        temperature=0.8, top_k=50, top_p=0.8, repetition_penalty=2.0, pos_mode="ref_kv_quirk",
+                        use_graph=True):
+        """ONE sequence decoded block-wise: ≙ the token stream of `GPT2InferenceModel.generate_stream` /
+        `sample_stream` (autoregressive.py:565-574, stream_generator.py:916-1000), which yields every sampled token
+        INCLUDING the stop token and ends after it (or after `max_new` tokens). A generator of `(codes, ended)`:
+        `codes` = int32 [n] all tokens so far, after the first `first_block` tokens, then every `block` tokens, and a
+        last time when the stream has ended (`ended` True; the stop token, if any, is the last element)."""
+        Nmax = int(max_new)
+        sp = self._sampling(temperature, top_k, top_p, repetition_penalty, pos_mode)
+        st = self._begin(cond_latent, text_tokens, 1, Nmax, uniforms, seed, sp)
+        if use_graph and Nmax > 1:
+            self._ensure_graph(st, sp)
+        stop = self.cfg.stop_mel_token
+        have = 1                       # tokens sampled so far (the first one comes from the prefill logits)
+        target = max(1, int(first_block))
+        blk = max(1, int(block))
+        while True:
+            want = min(target, Nmax)
+            for _ in range(want - have):
+                if use_graph:
+                    st["graph"].replay()
+                else:
+                    self._decode_step(st, sp)
+            if use_graph and want > have:
+                lib.add_calls((want - have) * st["graph_calls"])
+            have = max(have, want)
+            row = st["codes"][0, :have].clone()            # (synchronises through .tolist() below)
+            if st["fused"] and have > 1:
+                self._check_step_flag(st)
+            hit = (row == stop).nonzero()
+            if hit.numel() > 0:
+                yield row[: int(hit[0].item()) + 1], True
+                return
+            if have >= Nmax:
+                yield row, True
+                return
+            yield row, False
+            target = have + blk
 
     # ------------------------------------------------------------------ teacher-forced passes
     def _forward_sequences(self, emb_fn, nseq, T):
@@ -388,3 +446,30 @@ class AREngine:
         out = torch.empty(M, D, dtype=torch.float32, device=dev)
         lib.layernorm(x, M, D, self.w.lnf_g, self.w.lnf_b, self.w.fn_g, self.w.fn_b, out_f32=out)
         return out.view(k, T, D)[:, Pm:Pm + L].contiguous()
+
+    def stream_latents(self, cond_latent, text_tokens, codes):
+        """The latents the streaming generator yields next to its tokens (stream_generator.py:982:
+        `final_norm(hidden_states[-1][:, -1])` of the step that SAMPLED token i, i.e. of the input [start, c_0 ... c_{i-1}]
+        with the KV-cache position rule of GPT2InferenceModel.forward). codes int [n] -> fp32 [n, D], one teacher-forced
+        pass over the prefix instead of n cached steps (same numbers: the decode-step parity tests pin the two forms
+        against each other)."""
+        cfg, D, dev = self.cfg, self.D, self.dev
+        codes = codes.reshape(-1)
+        n = int(codes.numel())
+        ids = self._prompt_ids(text_tokens)
+        Pm = len(ids) + 1
+        T = Pm + n
+
+        def emb(x):
+            tid = torch.tensor(ids, dtype=torch.int32, device=dev)
+            tpos = torch.arange(len(ids), dtype=torch.int32, device=dev)
+            lib.embed(tid, tpos, len(ids), D, self.w.text_emb, self.w.text_pos, x[1:Pm])
+            x[0] = cond_latent.reshape(-1).to(dev)
+            mid = torch.cat([torch.full((1,), cfg.start_mel_token, dtype=torch.int32, device=dev),
+                             codes[: n - 1].to(device=dev, dtype=torch.int32)]).contiguous()
+            mpos = torch.tensor([(j + 1 if j >= 1 else j) for j in range(n)], dtype=torch.int32, device=dev)
+            lib.embed(mid, mpos, n, D, self.w.mel_emb, self.w.mel_pos, x[Pm:])
+        x = self._forward_sequences(emb, 1, T)
+        out = torch.empty(T, D, dtype=torch.float32, device=dev)
+        lib.layernorm(x, T, D, self.w.lnf_g, self.w.lnf_b, self.w.fn_g, self.w.fn_b, out_f32=out)
+        return out[Pm:].contiguous()

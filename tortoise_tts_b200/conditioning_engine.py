@@ -96,6 +96,9 @@ class ConditioningEngine:
         self.w_init = _bf(_pad_k(sd_ar["conditioning_encoder.init.weight"], self.kpad_ar), dev)
         self.b_init = _f(sd_ar["conditioning_encoder.init.bias"], dev)
         self.ar_attn = [_AttnW(sd_ar, f"conditioning_encoder.attn.{i}.", D, cfg.ar_heads, dev) for i in range(cfg.cond_enc_blocks)]
+        self.ar_heads, self.diff_heads = cfg.ar_heads, H
+        if sd_diff is None:       # api_fast needs the autoregressive conditioning latent only (api_fast.py:225-246)
+            return
         # --- diffusion contextual embedder (diffusion_decoder.py:186-192)
         self.kpad_diff = 128
         self.w_c0 = _bf(_pad_k(sd_diff["contextual_embedder.0.weight"], self.kpad_diff), dev)
