@@ -143,27 +143,32 @@ def kernel_probes(tts, cfg, n_mel, B, P, iters=200):
     Hh, D, L = cfg.ar_heads, cfg.ar_dim, cfg.ar_layers
     mode = st["mode"]
     if st["fused"]:
-        hd = eng._step_handle(st, 1)
-        st["state"].zero_()
-        st["state"][0] = n_mel // 2
-        st["codes"].zero_()
+        # the decode workspace may be split into chains (TTB_AR_CHAINS): each chain launches these kernels on its own
+        # half of the candidates, so the probe times one chain's launch and counts it once per chain
+        ch = st["chains"][0]
+        nch, Bc = len(st["chains"]), ch["B"]
+        hd = eng._step_handle(ch, 1)
+        ch["state"].zero_()
+        ch["state"][0] = n_mel // 2
+        ch["codes"].zero_()
         ms = timeit(lambda: hd.step(), flush=flush)
-        assert int(st["state"][2].item()) == 0, "ar_step_kernel timed out internally"
+        assert int(ch["state"][2].item()) == 0, "ar_step_kernel timed out internally"
         w_bytes = (L * 12 * D * D + cfg.number_mel_codes * D) * 2
-        kv_bytes = L * Hh * P * 128 * 2 + B * L * Hh * (n_mel // 2) * 128 * 2
-        out.append(dict(kernel="AR decode step kernel (B=%d, ctx=%d+%d, 30 layers + mel_head)" % (B, P, n_mel // 2),
+        kv_bytes = L * Hh * P * 128 * 2 + Bc * L * Hh * (n_mel // 2) * 128 * 2
+        out.append(dict(kernel="AR decode step kernel (B=%d, ctx=%d+%d, 30 layers + mel_head)" % (Bc, P, n_mel // 2),
                         bound="hbm", ms=ms, count=(n_mel - 1) if mode == "fused" else 0,
                         achieved=(w_bytes + kv_bytes) / ms / 1e6, peak=hbm, unit="GB/s", algorithmic_bytes=w_bytes + kv_bytes))
         # the attention kernel as the mixed mode launches it: all L layers back to back (every layer streams its own
-        # 450 MB slice of the 13.5 GB cache, so nothing is reused from the 126 MB L2 between launches), per-launch = / L
+        # slice of the 13.5 GB cache, so nothing is reused from the 126 MB L2 between launches), per-launch = / L
         def all_layers():
             for l in range(L):
                 hd.step(phase_mask=4, layer_begin=l, layer_end=l + 1)
         ms_a = timeit(all_layers, flush=flush) / L
-        nbytes = B * Hh * (n_mel // 2) * 128 * 2 + Hh * P * 128 * 2
-        out.append(dict(kernel="AR decode attention kernel (ar_attn_only_kernel, one layer, B=%d, ctx=%d+%d; mean of %d "
-                               "back-to-back layers)" % (B, P, n_mel // 2, L), bound="hbm", ms=ms_a,
-                        count=L * (n_mel - 1) if mode == "mixed" else 0,
+        nbytes = Bc * Hh * (n_mel // 2) * 128 * 2 + Hh * P * 128 * 2
+        kname = "ar_attn_compact_kernel" if ch.get("compact") else "ar_attn_only_kernel"
+        out.append(dict(kernel="AR decode attention kernel (%s, one layer, B=%d, ctx=%d+%d; mean of %d "
+                               "back-to-back layers)" % (kname, Bc, P, n_mel // 2, L), bound="hbm", ms=ms_a,
+                        count=nch * L * (n_mel - 1) if mode == "mixed" else 0,
                         achieved=nbytes / ms_a / 1e6, peak=hbm, unit="GB/s", algorithmic_bytes=nbytes))
     else:
         ck = torch.zeros(B, Hh, n_mel, 64, device=dev, dtype=torch.bfloat16)

@@ -58,6 +58,9 @@ typedef struct TtbGemmArgs {
   int gn_groups;
   int tap_dilation;     /* > 1: conv taps are tap_dilation rows apart (dilated Conv1d; `pad` stays in rows, e.g.
                            dilation * (k - 1) / 2); 0 / 1 = adjacent rows */
+  int w_static;         /* 1 = W is a parameter: no kernel enqueued earlier on the stream writes it. The one-tile kernel
+                           may then fetch its weight tiles before it waits for the preceding kernel (programmatic
+                           dependent launch); results do not change */
 } TtbGemmArgs;
 
 /* nn.Linear / HF Conv1D / nn.Conv1d(k=1,3) as one tcgen05 GEMM with fused bias/activation/residual.
@@ -191,6 +194,9 @@ typedef struct TtbArStepArgs {
   int debug_layer_begin, debug_layer_end;  /* debug_layer_end > 0: run layers [begin, end) only */
   int debug_phase_mask;                    /* != 0: subset of phases (bit 0 embed+ln_1, 1 c_attn, 2 attention, 3 c_proj, 4 ln_2,
                                               5 c_fc, 6 mlp.c_proj, 7 next ln_1 / final norms, 8 mel_head) - tests and probes */
+  int attn_compact;                        /* 1: the attention-only launch (debug_phase_mask = 4, one layer) runs in 8-warp CTAs
+                                              whose shared memory is sized to the prompt (~118 KB at P = 174), so that CTAs of
+                                              another stream fit beside them (two decode chains); same results */
 } TtbArStepArgs;
 int ttb_ar_step_workspace(const TtbArStepArgs* args, long long* part_floats, long long* table_bytes, long long* sync_bytes);
 int ttb_ar_step_setup(const TtbArStepArgs* args, void* stream);      /* synchronous; once per (weights, workspace, B) */

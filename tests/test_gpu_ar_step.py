@@ -246,3 +246,48 @@ def test_step_full_depth_vs_oracle():
     r = _rel(seen, want)
     report("ar_step full-depth decode logits vs oracle", r)
     assert r < 0.03
+
+
+@pytest.mark.parametrize("B", [256, 128])
+def test_two_chains_match_one_chain(B):
+    """TTB_AR_CHAINS=2: the candidates decoded as two half-batches on two streams inside one (captured) step, with the
+    attention in compact CTAs (`ar_attn_compact_kernel`, TtbArStepArgs.attn_compact). Every kernel of the step is
+    row-independent, so codes and the logits the sampler sees must equal the one-chain run BIT FOR BIT, eager and as a
+    graph replay (full width, 2 layers, prompt 174)."""
+    import os
+    from tortoise_tts_b200.config import ModelConfig
+    from tortoise_tts_b200.synth import synth_all
+    from tortoise_tts_b200 import ar_engine
+    cfg = ModelConfig.medium()
+    sd = synth_all(cfg, seed=1, suppress_stop=True)["autoregressive"]
+    torch.manual_seed(0)
+    text = torch.randint(1, 255, (169,)).tolist() + [0]
+    cond = torch.randn(1, cfg.ar_dim)
+    N = 24
+    u = torch.rand(B, N)
+    E = ar_engine.AREngine
+    saved = (E.MODE, E.CHAINS, E.CHAINS_MIN_B)
+    runs = {}
+    # one warp per (candidate, head) stream in both runs: with fewer candidates per CTA the planner would otherwise split
+    # a stream over a team of warps, whose merge rounds differently (still correct, no longer bit-identical)
+    os.environ["TTB_AR_STEP_TEAM"] = "1"
+    try:
+        E.MODE, E.CHAINS_MIN_B = "mixed", 64
+        for nch in (1, 2):
+            E.CHAINS = nch
+            eng = E(sd, cfg)
+            tr = []
+            codes = eng.generate(cond, text, B, N, uniforms=u, trace_logits=tr).cpu()
+            assert len(eng._dec["chains"]) == nch and bool(eng._dec["chains"][0]["compact"]) == (nch == 2)
+            codes_g = eng.generate(cond, text, B, N, uniforms=u, use_graph=True).cpu()
+            codes_g2 = eng.generate(cond, text, B, N, uniforms=u, use_graph=True).cpu()
+            assert torch.equal(codes_g, codes) and torch.equal(codes_g2, codes), "graph replay differs (chains=%d)" % nch
+            runs[nch] = (codes, torch.stack([x.cpu() for x in tr], 1))
+            del eng
+    finally:
+        E.MODE, E.CHAINS, E.CHAINS_MIN_B = saved
+        os.environ.pop("TTB_AR_STEP_TEAM", None)
+    assert torch.equal(runs[1][0], runs[2][0])
+    d = (runs[1][1] - runs[2][1]).abs().max().item()
+    report("two decode chains vs one: max |logit difference| B=%d" % B, d)
+    assert d == 0.0

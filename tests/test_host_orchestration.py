@@ -81,6 +81,29 @@ def test_ar_stream(env):
         assert _rel(got, want) < 0.03
 
 
+def test_ar_two_chains_equal_one(env, monkeypatch):
+    """TTB_AR_CHAINS=2 (two half-batches decoded as independent chains inside one step) must reproduce the one-chain
+    result bit for bit: the sampler is keyed by the candidate's own row of the uniforms table and its own KV cache."""
+    from tortoise_tts_b200.ar_engine import AREngine
+    cfg, sds, g = env
+    text = g["text"].tolist()
+    torch.manual_seed(2)
+    u = torch.rand(4, 7)
+    monkeypatch.setattr(AREngine, "MODE", "mixed")
+    monkeypatch.setattr(AREngine, "CHAINS_MIN_B", 2)
+    outs = []
+    for n in (1, 2):
+        monkeypatch.setattr(AREngine, "CHAINS", n)
+        eng = AREngine(sds["autoregressive"], cfg, device="cpu")
+        tr = []
+        codes = eng.generate(g["ar_cond"], text, 4, 7, uniforms=u, use_graph=False, trace_logits=tr)
+        assert len(eng._dec["chains"]) == n and eng._dec["mode"] == "mixed"
+        outs.append((codes, torch.stack(tr, 1)))
+    assert torch.equal(outs[0][0], outs[1][0])
+    # (the emulation's torch matmuls round differently for 2 and 4 rows; the kernels are row-independent)
+    assert (outs[0][1] - outs[1][1]).abs().max().item() < 1e-3
+
+
 def _fast_facade(cfg, sds):
     """api_fast.TextToSpeech on the CPU emulation (the constructor insists on a CUDA device: fields set by hand)."""
     from tortoise_tts_b200 import api_fast

@@ -73,15 +73,18 @@ def main():
     ar._dec = None
     st = ar._decode_state(B, len(toks) + 4, N)
     ar._prefill(cond, toks, st)
-    st["codes"].fill_(100)
-    st["state"][0] = N // 2
+
+    def mid_run():
+        for ch in st["chains"]:
+            ch["codes"].fill_(100)
+            ch["state"][0] = N // 2
     sp = dict(temperature=0.8, top_k=50, top_p=0.8, rep_penalty=2.0, pos_mode=1)
     for _ in range(2):
-        st["state"][0] = N // 2
+        mid_run()
         ar._decode_step(st, sp)
     rec = []
     saved = instrument(lib, rec)
-    st["state"][0] = N // 2
+    mid_run()
     ar._decode_step(st, sp)
     summarize(rec, "AR decode step at ctx %d+%d, B=%d" % (st["P"], N // 2, B))
     for n, fn in saved.items():

@@ -69,6 +69,15 @@ class AREngine:
     # replaced by the persistent kernel's attention phase (one launch, 54 us). "auto" picks by batch size.
     MODE = _os.environ.get("TTB_AR_MODE", "auto")            # auto | fused | mixed | perop
     FUSED_MAX_B = int(_os.environ.get("TTB_AR_FUSED_MAX_B", "40"))
+    # TTB_AR_CHAINS=2: in mixed mode the candidates are decoded as TWO independent half-batches on two streams inside
+    # one captured step. Every kernel of the chain LN -> c_attn -> attention -> c_proj -> LN -> c_fc -> mlp.c_proj is
+    # bound by its own latency except the attention (HBM-bound), so the chain of one half fills the bubbles of the
+    # other; the attention then runs in compact CTAs (lib.ArStep attn_compact) that leave room for a GEMM CTA per SM.
+    # which decode GEMMs may fetch their weights ahead of griddepcontrol.wait (TtbGemmArgs.w_static): "ln" = the ones that
+    # follow a LayerNorm (which triggers its dependents early), "all", "none"
+    WSTATIC = _os.environ.get("TTB_AR_WSTATIC", "ln")
+    CHAINS = int(_os.environ.get("TTB_AR_CHAINS", "2"))     # measured: AR 1157 -> 1092 ms at 256 candidates, 860 -> 840 at 128
+    CHAINS_MIN_B = int(_os.environ.get("TTB_AR_CHAINS_MIN_B", "128"))
     SPLITK_PROJ = 2     # attn.c_proj  (K = D):   32 n-tiles x 2 m-tiles x 2 splits = 128 CTAs at D=1024, B=256
     SPLITK_PROJ2 = 4    # mlp.c_proj   (K = 4D):  32 x 2 x 4 = 256 CTAs
 
@@ -135,44 +144,62 @@ class AREngine:
         key = (B, P, Nmax)
         if self._dec is not None and self._dec["key"] == key:
             return self._dec
-        cfg, D, H, dev = self.cfg, self.D, self.H, self.dev
-        L = cfg.ar_layers
-        st = dict(key=key, P=P, B=B, Nmax=Nmax)
-        st["px"] = torch.empty(P, D, dtype=torch.float32, device=dev)
-        st["pws"] = self._alloc_trunk(P)
-        ok = bool(self.FUSED) and lib.ar_step_supported(B, D, H, P)
+        self._dec = None                  # release the previous workspace (KV caches) before allocating the next
+        cfg, D, dev = self.cfg, self.D, self.dev
+        ok = bool(self.FUSED) and lib.ar_step_supported(B, D, self.H, P)
         mode = self.MODE if ok else "perop"
         if mode == "auto":
             mode = "fused" if B <= self.FUSED_MAX_B else "mixed"
-        st["mode"] = mode
-        st["fused"] = mode in ("fused", "mixed")           # interleaved K|V cache layout (csrc/ar_step.cu)
+        nch = self.CHAINS if (mode == "mixed" and self.CHAINS > 1 and B >= self.CHAINS_MIN_B and B % self.CHAINS == 0) else 1
+        st = dict(key=key, P=P, B=B, Nmax=Nmax, mode=mode, fused=mode in ("fused", "mixed"))
+        L, H = cfg.ar_layers, self.H
+        # ---- prompt prefill (shared by every candidate and every chain)
+        st["px"] = torch.empty(P, D, dtype=torch.float32, device=dev)
+        st["pws"] = self._alloc_trunk(P)
         if st["fused"]:
             # K and V of a position adjacent: one (candidate, head) stream is one contiguous byte range (csrc/ar_step.cu)
             st["pkv"] = torch.empty(L, H, P, 2, 64, dtype=torch.bfloat16, device=dev)
-            st["ckv"] = torch.zeros(L, B, H, Nmax, 2, 64, dtype=torch.bfloat16, device=dev)
         else:
             st["pk"] = torch.empty(L, H, P, 64, dtype=torch.bfloat16, device=dev)
             st["pv"] = torch.empty(L, H, P, 64, dtype=torch.bfloat16, device=dev)
-            st["ck"] = torch.zeros(L, B, H, Nmax, 64, dtype=torch.bfloat16, device=dev)
-            st["cv"] = torch.zeros(L, B, H, Nmax, 64, dtype=torch.bfloat16, device=dev)
-        st["x"] = torch.empty(B, D, dtype=torch.float32, device=dev)
-        st["ws"] = self._alloc_trunk(B)
-        st["hn"] = torch.empty(max(B, 1), D, dtype=torch.bfloat16, device=dev)
-        st["att_o"] = torch.zeros(2, B, D, dtype=torch.float32, device=dev)      # [prefix | candidate] partial rows
-        st["att_lse"] = torch.zeros(2, B, H, dtype=torch.float32, device=dev)
-        st["part_a"] = torch.zeros(max(self.SPLITK_PROJ, 2), B, D, dtype=torch.float32, device=dev)
-        st["part_b"] = torch.zeros(max(self.SPLITK_PROJ2, 2), B, D, dtype=torch.float32, device=dev)
-        st["logits"] = torch.empty(B, self.V, dtype=torch.float32, device=dev)
-        st["state"] = torch.zeros(64, dtype=torch.int32, device=dev)
-        st["codes"] = torch.empty(B, Nmax, dtype=torch.int32, device=dev)
-        st["seen"] = torch.zeros(B, (self.V + 31) // 32, dtype=torch.int32, device=dev)
-        st["finished"] = torch.zeros(B, dtype=torch.int32, device=dev)
-        st["uniforms"] = torch.empty(B, Nmax, dtype=torch.float32, device=dev)
+        st["hn"] = torch.empty(1, D, dtype=torch.bfloat16, device=dev)
+        st["logits"] = torch.empty(1, self.V, dtype=torch.float32, device=dev)
+        # ---- decode workspaces: one per chain (contiguous candidate ranges)
+        per = B // nch
+        st["chains"] = [self._chain_state(st, per, c * per, compact=nch > 1) for c in range(nch)]
+        st["sides"] = [torch.cuda.Stream(device=dev) for _ in range(nch - 1)] if dev.type == "cuda" else []
         st["graph"] = None
         st["graph_params"] = None
-        st["step_handles"] = {}
         self._dec = st
         return st
+
+    def _chain_state(self, st, B, b0, compact=False):
+        """Decode workspace of candidates [b0, b0 + B): residual stream, trunk buffers, candidate KV cache, sampler state."""
+        cfg, D, H, dev = self.cfg, self.D, self.H, self.dev
+        L, Nmax = cfg.ar_layers, st["Nmax"]
+        ch = dict(B=B, b0=b0, P=st["P"], Nmax=Nmax, mode=st["mode"], fused=st["fused"], compact=compact)
+        if st["fused"]:
+            ch["pkv"] = st["pkv"]
+            ch["ckv"] = torch.zeros(L, B, H, Nmax, 2, 64, dtype=torch.bfloat16, device=dev)
+        else:
+            ch["pk"], ch["pv"] = st["pk"], st["pv"]
+            ch["ck"] = torch.zeros(L, B, H, Nmax, 64, dtype=torch.bfloat16, device=dev)
+            ch["cv"] = torch.zeros(L, B, H, Nmax, 64, dtype=torch.bfloat16, device=dev)
+        ch["x"] = torch.empty(B, D, dtype=torch.float32, device=dev)
+        ch["ws"] = self._alloc_trunk(B)
+        ch["hn"] = torch.empty(max(B, 1), D, dtype=torch.bfloat16, device=dev)
+        ch["att_o"] = torch.zeros(2, B, D, dtype=torch.float32, device=dev)      # [prefix | candidate] partial rows
+        ch["att_lse"] = torch.zeros(2, B, H, dtype=torch.float32, device=dev)
+        ch["part_a"] = torch.zeros(max(self.SPLITK_PROJ, 2), B, D, dtype=torch.float32, device=dev)
+        ch["part_b"] = torch.zeros(max(self.SPLITK_PROJ2, 2), B, D, dtype=torch.float32, device=dev)
+        ch["logits"] = torch.empty(B, self.V, dtype=torch.float32, device=dev)
+        ch["state"] = torch.zeros(64, dtype=torch.int32, device=dev)
+        ch["codes"] = torch.empty(B, Nmax, dtype=torch.int32, device=dev)
+        ch["seen"] = torch.zeros(B, (self.V + 31) // 32, dtype=torch.int32, device=dev)
+        ch["finished"] = torch.zeros(B, dtype=torch.int32, device=dev)
+        ch["uniforms"] = torch.empty(B, Nmax, dtype=torch.float32, device=dev)
+        ch["step_handles"] = {}
+        return ch
 
     def _step_handle(self, st, pos_mode):
         """The one-kernel decode step bound to this workspace (tensor maps are built once per workspace + position rule)."""
@@ -183,12 +210,31 @@ class AREngine:
                             pos_mode=pos_mode, layers=w.layers, w_head=w.w_head, b_head=w.b_head, lnf_g=w.lnf_g,
                             lnf_b=w.lnf_b, fn_g=w.fn_g, fn_b=w.fn_b, mel_emb=w.mel_emb, mel_pos=w.mel_pos,
                             codes=st["codes"], ld_codes=st["Nmax"], state=st["state"], x=st["x"], a=ws["a"], qkv=ws["qkv"],
-                            o=ws["o"], h=ws["h"], hn=st["hn"], logits=st["logits"], prefix_kv=st["pkv"], cand_kv=st["ckv"])
+                            o=ws["o"], h=ws["h"], hn=st["hn"], logits=st["logits"], prefix_kv=st["pkv"], cand_kv=st["ckv"],
+                            attn_compact=bool(st.get("compact")))
             st["step_handles"][pos_mode] = hd
         return hd
 
     def _decode_step(self, st, sp):
-        """One trunk pass for the last sampled token of every candidate + fused sampling of the next one."""
+        """One decode step of every chain: chain 0 on the current stream, every other chain on its own side stream (forked
+        and joined with events, so the whole step is still ONE capturable unit)."""
+        chains = st["chains"]
+        if len(chains) == 1 or not st["sides"]:
+            for ch in chains:
+                self._chain_step(ch, sp)
+            return
+        cur = torch.cuda.current_stream()
+        for side in st["sides"]:
+            side.wait_stream(cur)
+        self._chain_step(chains[0], sp)
+        for ch, side in zip(chains[1:], st["sides"]):
+            with torch.cuda.stream(side):
+                self._chain_step(ch, sp)
+        for side in st["sides"]:
+            cur.wait_stream(side)
+
+    def _chain_step(self, st, sp):
+        """One trunk pass for the last sampled token of every candidate of one chain + fused sampling of the next one."""
         B, P, Nmax, D, H = st["B"], st["P"], st["Nmax"], self.D, self.H
         x, ws = st["x"], st["ws"]
         if st["mode"] == "fused":
@@ -209,29 +255,32 @@ class AREngine:
         s2 = min(self.SPLITK_PROJ2, 4 * kb)
         pa, pb = st["part_a"], st["part_b"]
         wide = dict(tile_n=64, variant=3) if (self.DECODE_WIDE and not cl) else dict(tile_n=32)
+        ws_ln, ws_all = self.WSTATIC in ("ln", "all"), self.WSTATIC == "all"
         prev = None   # (partials, nsplit, bias) of the previous layer's mlp.c_proj, folded into the next LayerNorm
         for l, lw in enumerate(self.w.layers):
             if prev is None:
                 lib.layernorm(x, B, D, lw["ln1_g"], lw["ln1_b"], out_bf16=ws["a"])
             else:
                 lib.residual_layernorm(x, B, D, prev[0], prev[1], B * D, prev[2], lw["ln1_g"], lw["ln1_b"], out_bf16=ws["a"])
-            lib.gemm(ws["a"], lw["wqkv"], M=B, N=3 * D, K=D, bias=lw["bqkv"], out_bf16=ws["qkv"], cluster=cl, **wide)
+            lib.gemm(ws["a"], lw["wqkv"], M=B, N=3 * D, K=D, bias=lw["bqkv"], out_bf16=ws["qkv"], cluster=cl, w_static=ws_ln,
+                     **wide)
             if hd is not None:
                 hd.step(phase_mask=4, layer_begin=l, layer_end=l + 1)     # attention phase of the persistent kernel
             else:
                 lib.ar_decode_attention(ws["qkv"], st["pk"][l], st["pv"][l], st["ck"][l], st["cv"][l], st["state"], B, H,
                                         P, Nmax, ws["o"], st["att_o"], st["att_lse"])
-            lib.gemm(ws["o"], lw["wproj"], M=B, N=D, K=D, out_f32=pa, outf_bstride=B * D, tile_n=32, splitk=max(s1, 2), cluster=cl)
+            lib.gemm(ws["o"], lw["wproj"], M=B, N=D, K=D, out_f32=pa, outf_bstride=B * D, tile_n=32, splitk=max(s1, 2), cluster=cl,
+                     w_static=ws_all)
             lib.residual_layernorm(x, B, D, pa, self._nsplit(kb, max(s1, 2)), B * D, lw["bproj"], lw["ln2_g"], lw["ln2_b"],
                                    out_bf16=ws["a"])
             lib.gemm(ws["a"], lw["wfc"], M=B, N=4 * D, K=D, bias=lw["bfc"], act=lib.ACT_GELU_NEW, out_bf16=ws["h"],
-                     cluster=cl, **wide)
+                     cluster=cl, w_static=ws_ln, **wide)
             lib.gemm(ws["h"], lw["wproj2"], M=B, N=D, K=4 * D, out_f32=pb, outf_bstride=B * D, tile_n=32, cluster=cl,
-                     splitk=max(s2, 2))
+                     splitk=max(s2, 2), w_static=ws_all)
             prev = (pb, self._nsplit(4 * kb, max(s2, 2)), lw["bproj2"])
         lib.residual_layernorm(x, B, D, prev[0], prev[1], B * D, prev[2], self.w.lnf_g, self.w.lnf_b, self.w.fn_g,
                                self.w.fn_b, out_bf16=st["hn"])
-        lib.gemm(st["hn"], self.w.w_head, M=B, N=self.V, K=D, bias=self.w.b_head, out_f32=st["logits"])
+        lib.gemm(st["hn"], self.w.w_head, M=B, N=self.V, K=D, bias=self.w.b_head, out_f32=st["logits"], w_static=ws_ln)
         lib.ar_sample(st["logits"], self.V, self.V, B, st["uniforms"], Nmax, st["seen"], st["codes"], Nmax,
                       st["finished"], st["state"], sp["temperature"], sp["top_k"], sp["top_p"], sp["rep_penalty"],
                       self.cfg.stop_mel_token, advance=True)
@@ -244,24 +293,27 @@ class AREngine:
         if uniforms is None:
             g = torch.Generator(device=dev)
             g.manual_seed(0 if seed is None else int(seed))
-            st["uniforms"].copy_(torch.rand(B, Nmax, generator=g, device=dev))
-        else:
-            st["uniforms"].copy_(uniforms.to(device=dev, dtype=torch.float32))
-        st["state"].zero_()
-        st["finished"].zero_()
-        st["codes"].fill_(cfg.stop_mel_token)
-        st["seen"].zero_()
-        # HF's repetition penalty sees the fake prompt ids {1, start_mel} (autoregressive.py:546-548)
-        st["seen"][:, 0] = 2
-        w, bit = divmod(cfg.start_mel_token, 32)
-        st["seen"][:, w] |= (1 << bit) if bit < 31 else -(1 << 31)
+            uniforms = torch.rand(B, Nmax, generator=g, device=dev)
+        uniforms = uniforms.to(device=dev, dtype=torch.float32)
         self._prefill(cond_latent, text_tokens, st)
         if trace_logits is not None:   # parity hook (eager mode): logits the sampler sees at every step
             trace_logits.append(st["logits"][:1].expand(B, -1).clone())
-        lib.ar_sample(st["logits"], 0, self.V, B, st["uniforms"], Nmax, st["seen"], st["codes"], Nmax, st["finished"],
-                      st["state"], sp["temperature"], sp["top_k"], sp["top_p"], sp["rep_penalty"], cfg.stop_mel_token,
-                      advance=True)
+        w, bit = divmod(cfg.start_mel_token, 32)
+        for ch in st["chains"]:
+            ch["uniforms"].copy_(uniforms[ch["b0"]: ch["b0"] + ch["B"]])
+            ch["state"].zero_()
+            ch["finished"].zero_()
+            ch["codes"].fill_(cfg.stop_mel_token)
+            ch["seen"].zero_()
+            # HF's repetition penalty sees the fake prompt ids {1, start_mel} (autoregressive.py:546-548)
+            ch["seen"][:, 0] = 2
+            ch["seen"][:, w] |= (1 << bit) if bit < 31 else -(1 << 31)
+            lib.ar_sample(st["logits"], 0, self.V, ch["B"], ch["uniforms"], Nmax, ch["seen"], ch["codes"], Nmax,
+                          ch["finished"], ch["state"], sp["temperature"], sp["top_k"], sp["top_p"], sp["rep_penalty"],
+                          cfg.stop_mel_token, advance=True)
         return st
+
+    _SNAP = ("state", "codes", "seen", "finished")
 
     def _ensure_graph(self, st, sp):
         """The decode step of this workspace as a CUDA graph (captured once per workspace + sampling parameters)."""
@@ -269,11 +321,15 @@ class AREngine:
             return
         # warm-up once eagerly (module loading / attribute setting must not happen under capture),
         # then restore the sampler state and capture
-        snap = {k: st[k].clone() for k in ("state", "codes", "seen", "finished")}
+        snap = [{k: ch[k].clone() for k in self._SNAP} for ch in st["chains"]]
+
+        def restore():
+            for ch, sn in zip(st["chains"], snap):
+                for k, v in sn.items():
+                    ch[k].copy_(v)
         self._decode_step(st, sp)
         torch.cuda.synchronize()
-        for k, v in snap.items():
-            st[k].copy_(v)
+        restore()
         g = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -283,14 +339,23 @@ class AREngine:
                 self._decode_step(st, sp)
         st["graph_calls"] = lib.CALLS - c0
         torch.cuda.current_stream().wait_stream(side)
-        for k, v in snap.items():
-            st[k].copy_(v)
+        restore()
         st["graph"], st["graph_params"] = g, dict(sp)
 
     def _check_step_flag(self, st):
-        flag = int(st["state"][2].item())      # TtbArState.reserved[0]: set by a timed-out wait inside the step kernel
-        if flag:
-            raise lib.TtbError("ar_step_kernel: internal wait timed out (code %d); results are invalid" % flag)
+        for ch in st["chains"]:
+            flag = int(ch["state"][2].item())  # TtbArState.reserved[0]: set by a timed-out wait inside the step kernel
+            if flag:
+                raise lib.TtbError("ar_step_kernel: internal wait timed out (code %d); results are invalid" % flag)
+
+    @staticmethod
+    def _all_finished(st):
+        return all(int(ch["state"][1].item()) == 1 for ch in st["chains"])
+
+    @staticmethod
+    def _codes(st):
+        cs = [ch["codes"] for ch in st["chains"]]
+        return cs[0].clone() if len(cs) == 1 else torch.cat(cs, dim=0)
 
     @staticmethod
     def _sampling(temperature, top_k, top_p, repetition_penalty, pos_mode):
@@ -319,16 +384,16 @@ class AREngine:
                         st["graph"].replay()
                     lib.add_calls(n * st["graph_calls"])
                     done += n
-                    if done < steps and int(st["state"][1].item()) == 1:
+                    if done < steps and self._all_finished(st):
                         break
             else:
                 for i in range(steps):
                     self._decode_step(st, sp)
                     if trace_logits is not None:
-                        trace_logits.append(st["logits"].clone())
+                        trace_logits.append(torch.cat([ch["logits"] for ch in st["chains"]], dim=0).clone())
         if st["fused"] and steps > 0:
             self._check_step_flag(st)
-        return st["codes"].clone()
+        return self._codes(st)
 
     def generate_stream(self, cond_latent, text_tokens, max_new, first_block, block, uniforms=None, seed=None,
                         temperature=0.8, top_k=50, top_p=0.8, repetition_penalty=2.0, pos_mode="ref_kv_quirk",
@@ -357,7 +422,7 @@ class AREngine:
             if use_graph and want > have:
                 lib.add_calls((want - have) * st["graph_calls"])
             have = max(have, want)
-            row = st["codes"][0, :have].clone()            # (synchronises through .tolist() below)
+            row = st["chains"][0]["codes"][0, :have].clone()
             if st["fused"] and have > 1:
                 self._check_step_flag(st)
             hit = (row == stop).nonzero()

@@ -43,6 +43,7 @@ constexpr int AS_MAX_STAGES = 8;
 constexpr int AS_W_TILE_BYTES = 128 * 64 * 2;
 constexpr int AS_MAX_TILES = 512;                          // ticket counters (row tile x batch tile)
 constexpr int AS_SYNC_BAR_BYTES = 17 * 128;                // barrier epoch line + 16 arrival-counter lines
+constexpr int AS_COMPACT_WARPS = 8;                        // ar_attn_compact_kernel: 256 threads, ~118 KB at P = 174
 
 enum { G_QKV = 0, G_PROJ = 1, G_FC = 2, G_PROJ2 = 3, G_HEAD = 4 };
 enum { OUT_PARTIAL = 0, OUT_BF16 = 1, OUT_F32 = 2 };
@@ -80,6 +81,7 @@ struct AsParams {
   __nv_bfloat16* cand_kv;                 // [L][B][H][Nmax][2][64]
   unsigned long long* bar;                // [0] barrier epoch at launch; arrival slots at [16 * (1 + k)], k < 16
   unsigned int* tickets;                  // [AS_MAX_TILES]
+  int attn_data_bytes;                    // compact attention launch: rings of the active warps + the prompt of one head
 };
 
 // phase bits (phase_mask)
@@ -156,6 +158,13 @@ struct AsCtrl {                       // lives in the control block of shared me
   float merge[AS_WARPS][68];          // flash-decoding merge: acc[64], m, l
 };
 static_assert(sizeof(AsCtrl) <= AS_CTRL_BYTES, "control block too large");
+
+struct AsCtrlCompact {                // control block of ar_attn_compact_kernel: only what the attention phase touches
+  uint64_t ring_bar[AS_COMPACT_WARPS][4];
+  uint64_t prefix_bar;
+  float merge[AS_COMPACT_WARPS][68];
+};
+constexpr int AS_CTRL_COMPACT_BYTES = (int)((sizeof(AsCtrlCompact) + 127) & ~size_t(127));
 
 struct AsRole {                       // per-thread pipeline bookkeeping that survives across phases
   int stage;                          // GEMM smem ring position (producer and MMA thread keep identical copies)
@@ -682,7 +691,8 @@ TTB_DEVINL void mma_chunk(MmaState& st, const uint32_t* qb, uint32_t kt, uint32_
 // `wait_pdl`: the caller has NOT yet executed griddepcontrol.wait (ar_attn_only_kernel under programmatic dependent
 // launch): the prompt prefix and the first candidate tiles are requested first -- the caches were written by earlier
 // steps / this step's earlier kernels, only q and the new K / V come from the c_attn GEMM this launch depends on.
-TTB_DEVINL void attn_phase_mma(const AsParams& p, int layer, uint8_t* data, AsCtrl* ctrl, AsRole& rl, bool wait_pdl = false) {
+template <class CtrlT>
+TTB_DEVINL void attn_phase_mma(const AsParams& p, int layer, uint8_t* data, CtrlT* ctrl, AsRole& rl, bool wait_pdl = false) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* err = &p.state->reserved[0];
   const int B = p.B, H = p.H, P = p.P, Nmax = p.Nmax, D = p.H * 64;
@@ -1066,6 +1076,30 @@ __global__ void __launch_bounds__(AS_THREADS, 1) ar_attn_only_kernel(const __gri
   pdl_launch_dependents();
 }
 
+// The same phase in a CTA that leaves half of the SM free (TtbArStepArgs.attn_compact): 8 warps, shared memory = the
+// rings of the active warps + the prompt of ONE head + a small control block (111.5 KB at P = 174 instead of 225 KB), so
+// that a skinny-GEMM CTA (101 KB, 192 threads) of ANOTHER decode chain fits beside it -- or a second CTA of this kernel
+// (prompts up to 176 positions), which gives the SM its 16 concurrent KV streams back when the kernel has it to itself. Used when the candidates are decoded
+// as two independent half-batches on two streams (ar_engine.py, TTB_AR_CHAINS): the latency-bound GEMM / LayerNorm
+// chain of one half then overlaps the bandwidth-bound attention of the other.
+__global__ void __launch_bounds__(AS_COMPACT_WARPS * 32, 2) ar_attn_compact_kernel(const __grid_constant__ AsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* data = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  AsCtrlCompact* ctrl = reinterpret_cast<AsCtrlCompact*>(data + p.attn_data_bytes);
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < AS_COMPACT_WARPS; ++w)
+      for (int k = 0; k < 4; ++k) mbar_init(&ctrl->ring_bar[w][k], 1);
+    mbar_init(&ctrl->prefix_bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  AsRole rl;
+  rl.stage = 0; rl.phase = 0; rl.acc_par = 0; rl.prefix_par = 0; rl.bar_target = 0;
+  rl.ring_par[0] = rl.ring_par[1] = rl.ring_par[2] = rl.ring_par[3] = 0;
+  attn_phase_mma(p, p.layer_begin, data, ctrl, rl, true);
+  pdl_launch_dependents();
+}
+
 // prompt K/V from a qkv buffer [P, 3*H*64] into the interleaved prefix cache [H][P][K 64 | V 64]
 __global__ void ar_step_store_prefix_kernel(const __nv_bfloat16* __restrict__ qkv, int P, int H, __nv_bfloat16* __restrict__ pkv) {
   const int D = H * 64;
@@ -1083,6 +1117,7 @@ struct AsPlan {
   AsParams p;
   long long part_floats;
   int grid;
+  int compact_ctas;      // CTAs per SM the compact attention launch is sized for
 };
 
 static int as_num_sms() {
@@ -1143,12 +1178,16 @@ static int make_plan(const TtbArStepArgs& a, AsPlan& pl) {
   }
   pl.part_floats = pf;
   // attention decomposition
-  p.ncph = grid / a.H;
+  // (compact attention: up to two CTAs per SM, see ar_attn_compact_kernel; TTB_AR_COMPACT_CTAS=1 keeps one)
+  pl.compact_ctas = 1;
+  if (a.attn_compact) { pl.compact_ctas = env_int("TTB_AR_COMPACT_CTAS", 2); if (pl.compact_ctas < 1 || pl.compact_ctas > 2) pl.compact_ctas = 2; }
+  p.ncph = grid * pl.compact_ctas / a.H;
   if (p.ncph < 1) p.ncph = 1;
   if (p.ncph > a.B) p.ncph = a.B;
   const int max_items = (a.B + p.ncph - 1) / p.ncph;
   int wcap = env_int("TTB_AR_STEP_ATTN_WARPS", AS_WARPS);      // experiments: fewer concurrent streams, deeper rings
   if (wcap < 1 || wcap > AS_WARPS) wcap = AS_WARPS;
+  if (a.attn_compact && wcap > AS_COMPACT_WARPS) wcap = AS_COMPACT_WARPS;
   const int rounds = (max_items + wcap - 1) / wcap;
   p.ipr = (max_items + rounds - 1) / rounds;
   int team = 1;
@@ -1174,6 +1213,12 @@ static int make_plan(const TtbArStepArgs& a, AsPlan& pl) {
                 nact, a.P);
       return -1;
     }
+  }
+  p.attn_data_bytes = 0;
+  if (a.attn_compact) {
+    p.ring_ns = 2;
+    const long long need = (long long)p.ipr * p.team * p.ring_ns * p.ring_cp * AS_POS_BYTES + (long long)((a.P + 15) & ~15) * AS_POS_BYTES;
+    p.attn_data_bytes = (int)((need + 1023) & ~1023LL);
   }
   p.layer_begin = 0; p.layer_end = a.L; p.phase_mask = 0x1ff;
   if (a.debug_layer_end > 0) { p.layer_begin = a.debug_layer_begin; p.layer_end = a.debug_layer_end; }
@@ -1249,6 +1294,7 @@ extern "C" int ttb_ar_step_setup(const TtbArStepArgs* ap, void* stream) {
   if (!attr_set) {
     e = cudaFuncSetAttribute(ar_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AS_SMEM_TOTAL);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ar_attn_only_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AS_SMEM_TOTAL);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ar_attn_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AS_SMEM_TOTAL);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(ar_step_kernel)");
     attr_set = true;
   }
@@ -1277,6 +1323,15 @@ extern "C" int ttb_ar_decode_step(const TtbArStepArgs* ap, void* stream) {
   p.tickets = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(a.sync) + AS_SYNC_BAR_BYTES);
   if (p.phase_mask == PH_ATTN && p.layer_end == p.layer_begin + 1) {
     const int units = a.H * p.ncph;
+    if (a.attn_compact) {
+      if (p.attn_impl < 1) { set_error("ttb_ar_decode_step: attn_compact needs the tensor-core attention"); return -1; }
+      const int cgrid = pl.grid * pl.compact_ctas;
+      const cudaError_t lc = launch_pdl(ar_attn_compact_kernel, dim3(units < cgrid ? units : cgrid), dim3(AS_COMPACT_WARPS * 32),
+                                        (size_t)(p.attn_data_bytes + AS_CTRL_COMPACT_BYTES + 1024), st, p);
+      if (lc != cudaSuccess) return check_cuda(lc, "ar_attn_compact_kernel launch");
+      TTB_CHECK_LAUNCH("ar_attn_compact_kernel");
+      return 0;
+    }
     const cudaError_t la = launch_pdl(ar_attn_only_kernel, dim3(units < pl.grid ? units : pl.grid), dim3(AS_THREADS),
                                       (size_t)AS_SMEM_TOTAL, st, p);
     if (la != cudaSuccess) return check_cuda(la, "ar_attn_only_kernel launch");

@@ -199,6 +199,12 @@ TTB_DEVINL void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* ba
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// L2 prefetch of one box of a 3-D tensor map (no shared-memory destination, no barrier)
+TTB_DEVINL void tma_prefetch_l2_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 
 // ------------------------------------------------------------------ tcgen05
 TTB_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

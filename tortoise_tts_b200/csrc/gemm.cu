@@ -121,6 +121,7 @@ struct GemmEpilogue {
   int tap_dil;             // row distance between conv taps (dilation); 1 = plain
   float2* gn_part;         // GroupNorm partials [batch][groups][TTB_GN_SPLITS] of the output, or null (TtbGemmArgs.gn_partials)
   int gn_groups;
+  int wpre;                // TtbGemmArgs.w_static: W may be fetched before griddepcontrol.wait (one-tile kernel)
 };
 
 }  // namespace ttb
@@ -178,14 +179,46 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();                    // operands, residual and outputs belong to earlier kernels until here
+  // W is a parameter (TtbGemmArgs.w_static): under programmatic dependent launch its tiles do not have to wait for the
+  // kernels before this one. The first STAGES weight tiles go into the pipeline and the rest of this CTA's weight slab
+  // is pulled into L2 BEFORE griddepcontrol.wait; only the activation tiles are requested after it. For the skinny
+  // decode GEMMs (a 64 KB slab per CTA, ~1.5 us of DRAM latency in front of a 4 us main loop) the weights then stream
+  // while the previous kernel (LayerNorm, which triggers its dependents early) is still running.
+  int pre = 0;
+  if constexpr (!SPLIT_PRODUCER) {
+    if (ep.wpre && warp == 0 && lane == 0) {
+      pre = num_kb < STAGES ? num_kb : STAGES;
+      for (int kbi = 0; kbi < num_kb; ++kbi) {
+        const int kb = kb_begin + kbi;
+        const int tap = kb / kblocks_per_tap;
+        const int kk = (kb - tap * kblocks_per_tap) * BK;
+        if (kbi < pre) {
+          uint8_t* sb = smem + kbi * L::STAGE_BYTES + L::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[kbi], L::STAGE_BYTES);
+          tma_load_3d(sb, &map_b, &full_bar[kbi], tap * K + kk, n0, 0);
+        } else if (ep.wpre > 1) {
+          tma_prefetch_l2_3d(&map_b, tap * K + kk, n0, 0);
+        } else {
+          break;
+        }
+      }
+    }
+  }
+  pdl_wait();                    // activations, residual and outputs belong to earlier kernels until here
   if (tr && threadIdx.x == 0) tr[2] = global_timer_ns();
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int kbi = 0; kbi < num_kb; ++kbi) {
+      for (int kbi = 0; kbi < pre; ++kbi) {                 // activation halves of the stages started above
+        const int kb = kb_begin + kbi;
+        const int tap = kb / kblocks_per_tap;
+        const int kk = (kb - tap * kblocks_per_tap) * BK;
+        tma_load_3d(smem + kbi * L::STAGE_BYTES, &map_a, &full_bar[kbi], kk, m0 + tap * ep.tap_dil - pad, bz * a_batch_mul);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      for (int kbi = pre; kbi < num_kb; ++kbi) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         const int kb = kb_begin + kbi;
         const int tap = kb / kblocks_per_tap;
@@ -421,6 +454,10 @@ extern "C" int ttb_gemm(const TtbGemmArgs* gp, void* stream) {
   ep.res_bstride = g.res_bstride; ep.outf_bstride = g.outf_bstride; ep.outb_bstride = g.outb_bstride;
   ep.ldr = g.ldr; ep.ldo = g.ldo; ep.ldob = g.ldob; ep.act = g.act; ep.alpha = g.alpha;
   ep.gn_part = nullptr; ep.gn_groups = g.gn_groups;
+  static int wpre_on = -1;      // TTB_GEMM_WPREFETCH=0: A/B switch for the weight fetch ahead of griddepcontrol.wait
+  // 1 = the first STAGES weight tiles only, 2 = + L2 prefetch of the rest of the CTA's slab
+  if (wpre_on < 0) { const char* e = getenv("TTB_GEMM_WPREFETCH"); wpre_on = e ? atoi(e) : 1; }
+  ep.wpre = g.w_static ? wpre_on : 0;
   ep.tap_dil = g.tap_dilation > 1 ? g.tap_dilation : 1;
   if (ep.tap_dil > 1 && (g.cluster > 1 || g.variant == 6 || g.force_ref || g_gemm_impl == 1)) {
     set_error("ttb_gemm: tap_dilation is implemented by the one-tile and the persistent kernels only");

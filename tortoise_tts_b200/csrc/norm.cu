@@ -83,7 +83,12 @@ __global__ void __launch_bounds__(64)
 layernorm_warp_kernel(const float* x, int M, int D, const float* __restrict__ g1, const float* __restrict__ b1,
                       const float* __restrict__ g2, const float* __restrict__ b2, __nv_bfloat16* __restrict__ ob,
                       float* __restrict__ of, float* xw, const float* __restrict__ partials, int nsplit,
-                      long long split_stride, const float* __restrict__ rbias) {
+                      long long split_stride, const float* __restrict__ rbias, int early) {
+  // `early`: let the next kernel's CTAs start NOW (TTB_LN_EARLY, default on). In the decode step that kernel is a
+  // skinny GEMM with TtbGemmArgs.w_static: it runs its prologue and streams its weight tiles while this kernel works,
+  // and still waits (griddepcontrol.wait) for this grid to finish before it touches the normalised rows. This kernel
+  // needs no shared memory and few registers, so the early CTAs take nothing away from it.
+  if (early) pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 2 + (threadIdx.x >> 5);
@@ -111,7 +116,7 @@ layernorm_warp_kernel(const float* x, int M, int D, const float* __restrict__ g1
       *reinterpret_cast<float4*>(xw + row * D + (i * 32 + lane) * 4) = v[i];
     }
   }
-  pdl_launch_dependents();        // tail trigger: every load of this row is done
+  if (!early) pdl_launch_dependents();        // tail trigger: every load of this row is done
 #pragma unroll
   for (int pass = 0; pass < 2; ++pass) {
     const float* gg = pass == 0 ? g1 : g2;
@@ -381,9 +386,11 @@ static bool launch_ln_warp(const float* x, int M, int D, const float* g1, const 
   for (const void* p : ptrs)
     if (p && (reinterpret_cast<uintptr_t>(p) & 15)) return false;
   const dim3 grid((M + 1) / 2);
+  static int early = -1;
+  if (early < 0) { const char* e = getenv("TTB_LN_EARLY"); early = (e && e[0] == '0') ? 0 : 1; }
 #define TTB_LN_CASE(NV)                                                                                              \
   case NV: launch_pdl(layernorm_warp_kernel<NV>, grid, dim3(64), (size_t)0, st, x, M, D, g1, b1, g2, b2, ob, of, xw,  \
-                      partials, nsplit, split_stride, rbias); break;
+                      partials, nsplit, split_stride, rbias, early); break;
   switch (D / 128) {
     TTB_LN_CASE(1) TTB_LN_CASE(2) TTB_LN_CASE(3) TTB_LN_CASE(4) TTB_LN_CASE(5) TTB_LN_CASE(6) TTB_LN_CASE(7) TTB_LN_CASE(8)
     default: return false;

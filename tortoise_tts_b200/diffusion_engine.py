@@ -164,6 +164,8 @@ class DiffusionEngine:
         self.CL = cl if (cl in (2, 4) and (C // 128) % cl == 0) else 0
         # GroupNorm statistics taken in the epilogue of the producing GEMM (TTB_GN_FUSED=0: separate statistics pass)
         self.GN_FUSED = int(os.environ.get("TTB_GN_FUSED", "1"))
+        # the two CFG branches as two kernel chains on two streams instead of one batched pass (see _forward)
+        self.CHAINS = int(os.environ.get("TTB_DIFF_CHAINS", "0"))
 
     # ------------------------------------------------------------------ building blocks on [B, S, C] fp32 (in place)
     def _gn(self, x, B, S, g, b, ws, silu=False, ss=None, ss_row=None, out=None, ready=False):
@@ -237,8 +239,24 @@ class DiffusionEngine:
 
     # ------------------------------------------------------------------ one denoiser evaluation (both CFG branches)
     def _forward(self, st):
-        """DiffusionTts.forward (diffusion_decoder.py:262-322) for batch [cond, uncond] at the timestep selected by
-        the device-side call counter. Writes st['model_out'] [B, S, cout]."""
+        """Both CFG branches of one denoiser evaluation. Default: ONE batched pass (B = 2 in every launch). With
+        TTB_DIFF_CHAINS=1 the conditional and the unconditional branch run as two independent kernel chains on two
+        streams (forked / joined with events, still one capturable unit): the flash-attention kernel keeps the tensor
+        pipe ~17 % busy (it is bound by its softmax chain), so the other branch's GEMMs can use the rest of the SM."""
+        br = st.get("branches")
+        if not br:
+            return self._forward_one(st)
+        cur = torch.cuda.current_stream()
+        side = st["side"]
+        side.wait_stream(cur)
+        self._forward_one(br[0])
+        with torch.cuda.stream(side):
+            self._forward_one(br[1])
+        cur.wait_stream(side)
+
+    def _forward_one(self, st):
+        """DiffusionTts.forward (diffusion_decoder.py:262-322) for batch [cond, uncond] (or one of them) at the timestep
+        selected by the device-side call counter. Writes st['mo_local'] [B, S, cout]."""
         C, B, S, ws = self.C, st["B"], st["S"], st["ws"]
         xce = st["xce"]
         xce.copy_(st["code_emb_init"])
@@ -323,6 +341,14 @@ class DiffusionEngine:
         st["ss_all"] = torch.empty(len(self.res_all), iters, 2 * C, dtype=torch.float32, device=dev)
         st["graph"] = None
         st["xch"] = None
+        st["branches"] = None
+        if B == 2 and self.CHAINS and dev.type == "cuda":
+            # per-branch views of the batched buffers + a workspace of its own for each branch
+            st["branches"] = [dict(B=1, S=S, ws=self._alloc(1, S), xce=st["xce"][b:b + 1],
+                                   code_emb_init=st["code_emb_init"][b:b + 1], cat=st["cat"][b:b + 1], xm=st["xm"][b:b + 1],
+                                   mo_local=st["model_out"][b:b + 1], x_bf=st["x_bf"], ss_all=st["ss_all"],
+                                   counter=st["counter"]) for b in range(2)]
+            st["side"] = torch.cuda.Stream(device=dev)
         if pair is not None and st["model_out"].is_cuda:
             from . import parallel
             xch = parallel.PairExchange(pair[0], pair[1], S * self.cout, dev)

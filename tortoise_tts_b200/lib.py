@@ -26,7 +26,7 @@ class GemmArgs(C.Structure):
                 ("rows", C.c_int), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
                 ("taps", C.c_int), ("pad", C.c_int), ("batch", C.c_int), ("act", C.c_int),
                 ("alpha", C.c_float), ("tile_n", C.c_int), ("force_ref", C.c_int), ("splitk", C.c_int), ("cluster", C.c_int), ("variant", C.c_int),
-                ("gn_partials", C.c_void_p), ("gn_groups", C.c_int), ("tap_dilation", C.c_int)]
+                ("gn_partials", C.c_void_p), ("gn_groups", C.c_int), ("tap_dilation", C.c_int), ("w_static", C.c_int)]
 
 
 class AttnArgs(C.Structure):
@@ -60,7 +60,8 @@ class ArStepArgs(C.Structure):
                 ("state", C.c_void_p), ("x", C.c_void_p), ("a", C.c_void_p), ("qkv", C.c_void_p), ("o", C.c_void_p),
                 ("h", C.c_void_p), ("hn", C.c_void_p), ("part", C.c_void_p), ("logits", C.c_void_p),
                 ("prefix_kv", C.c_void_p), ("cand_kv", C.c_void_p), ("tables", C.c_void_p), ("sync", C.c_void_p),
-                ("debug_layer_begin", C.c_int), ("debug_layer_end", C.c_int), ("debug_phase_mask", C.c_int)]
+                ("debug_layer_begin", C.c_int), ("debug_layer_end", C.c_int), ("debug_phase_mask", C.c_int),
+                ("attn_compact", C.c_int)]
 
 
 _lib = None
@@ -131,7 +132,7 @@ def _f32(t):
 # ------------------------------------------------------------------ wrappers
 def gemm(A, W, *, M, N, K, bias=None, residual=None, out_f32=None, out_bf16=None, lda=None, rows=None, batch=1,
          a_bstride=0, res_bstride=0, outf_bstride=0, outb_bstride=0, ldr=None, ldo=None, ldob=None, taps=1, pad=0,
-         act=ACT_NONE, alpha=1.0, tile_n=0, force_ref=False, splitk=1, cluster=0, variant=0, gn_partials=None, gn_groups=0, tap_dilation=1):
+         act=ACT_NONE, alpha=1.0, tile_n=0, force_ref=False, splitk=1, cluster=0, variant=0, gn_partials=None, gn_groups=0, tap_dilation=1, w_static=False):
     """See include/ttb.h ttb_gemm. A: bf16 [batch, rows, lda]; W: bf16 [N, taps*K]. `gn_partials` (a groupnorm_scratch
     buffer): the epilogue also leaves the GroupNorm statistics of the output there (consumed by groupnorm_apply)."""
     _bf(A), _bf(W), _f32(bias), _f32(residual), _f32(out_f32), _bf(out_bf16)
@@ -150,6 +151,7 @@ def gemm(A, W, *, M, N, K, bias=None, residual=None, out_f32=None, out_bf16=None
     g.variant = variant
     g.gn_partials, g.gn_groups = _p(_f32(gn_partials)).value or 0, gn_groups
     g.tap_dilation = tap_dilation
+    g.w_static = 1 if w_static else 0
     _chk(load().ttb_gemm(C.byref(g), _stream()), "ttb_gemm")
 
 
@@ -235,7 +237,7 @@ class ArStep:
     keeps every tensor the kernel points at alive. `layers`: list of dicts with the keys of ARWeights.layers."""
 
     def __init__(self, *, B, D, H, L, V, P, Nmax, pos_mode, layers, w_head, b_head, lnf_g, lnf_b, fn_g, fn_b, mel_emb,
-                 mel_pos, codes, ld_codes, state, x, a, qkv, o, h, hn, logits, prefix_kv, cand_kv):
+                 mel_pos, codes, ld_codes, state, x, a, qkv, o, h, hn, logits, prefix_kv, cand_kv, attn_compact=False):
         dev = x.device
         self._keep = (layers, w_head, b_head, lnf_g, lnf_b, fn_g, fn_b, mel_emb, mel_pos, codes, state, x, a, qkv, o, h,
                       hn, logits, prefix_kv, cand_kv)
@@ -255,6 +257,7 @@ class ArStep:
         g.x, g.a, g.qkv, g.o = _f32(x).data_ptr(), _bf(a).data_ptr(), _bf(qkv).data_ptr(), _bf(o).data_ptr()
         g.h, g.hn, g.logits = _bf(h).data_ptr(), _bf(hn).data_ptr(), _f32(logits).data_ptr()
         g.prefix_kv, g.cand_kv = _bf(prefix_kv).data_ptr(), _bf(cand_kv).data_ptr()
+        g.attn_compact = 1 if attn_compact else 0
         pf, tb, sb = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
         _chk(load().ttb_ar_step_workspace(C.byref(g), C.byref(pf), C.byref(tb), C.byref(sb)), "ttb_ar_step_workspace")
         self.part = torch.zeros(max(pf.value, 4), dtype=torch.float32, device=dev)
