@@ -325,9 +325,10 @@ def run_engine(args):
         progress("probes done")
         dom = max(probes, key=lambda d: d["total_ms_per_utterance"])
         traffic, source = None, None
-        for key, val in ncu_traffic().items():
-            if dom["kernel"].startswith(key):
-                traffic, source = val["bytes"], val["source"]
+        best = ""
+        for key, val in ncu_traffic().items():          # the most specific (longest) matching probe-name prefix
+            if dom["kernel"].startswith(key) and len(key) > len(best):
+                best, traffic, source = key, val["bytes"], val["source"]
         line["roofline"] = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": round(dom["achieved"], 2),
                             "peak": dom["peak"], "unit": dom["unit"], "frac": round(dom["frac"], 4), "traffic": traffic,
                             "traffic_source": source, "peak_source": how, "launch_ms": round(dom["ms"], 4),

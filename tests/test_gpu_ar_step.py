@@ -20,7 +20,7 @@ def _rel(a, b):
     return (a.float() - b.float()).abs().max().item() / max(b.float().abs().max().item(), 1e-6)
 
 
-def _mk(B, D, H, L, V, P, Nmax, step, seed=0, pos_mode=1):
+def _mk(B, D, H, L, V, P, Nmax, step, seed=0, pos_mode=1, attn_compact=False):
     """Random weights / buffers for a stand-alone ArStep. Returns (handle, dict of tensors)."""
     from tortoise_tts_b200 import lib
     dev = "cuda"
@@ -48,7 +48,7 @@ def _mk(B, D, H, L, V, P, Nmax, step, seed=0, pos_mode=1):
              logits=torch.zeros(B, V, device=dev),
              prefix_kv=rn(L, H, P, 2, 64).to(torch.bfloat16), cand_kv=rn(L, B, H, Nmax, 2, 64).to(torch.bfloat16))
     t["state"][0] = step
-    hd = lib.ArStep(B=B, D=D, H=H, L=L, V=V, P=P, Nmax=Nmax, pos_mode=pos_mode, ld_codes=Nmax, **t)
+    hd = lib.ArStep(B=B, D=D, H=H, L=L, V=V, P=P, Nmax=Nmax, pos_mode=pos_mode, ld_codes=Nmax, attn_compact=attn_compact, **t)
     return hd, t
 
 

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Launches the hot kernels a few times at the bench shapes, for `ncu -k regex:<name>` captures (profiles/ncu_r02/).
-  python tools/prof_kernels.py fa | attn | step | step32 | lvc"""
+  python tools/prof_kernels.py fa | attn | attnc | step | step32 | lvc      (attnc = the compact attention kernel of the
+  two-chain decode step at its batch of 128 candidates)"""
 import os
 import sys
 
@@ -21,12 +22,12 @@ def main():
         bias = _rel_pos_table(torch.randn(32, H, device="cuda"), S, 8.0)
         for _ in range(4):
             lib.attention(qkv, o, nseq=2, T=S, H=H, ld=3 * C, ldo=C, k_off=C, v_off=2 * C, scale=0.125, bias=bias, bias_sat=64)
-    elif what in ("attn", "step", "step32"):
+    elif what in ("attn", "attnc", "step", "step32"):
         from test_gpu_ar_step import _mk
-        B = 32 if what == "step32" else 256
-        hd, t = _mk(B, 1024, 16, 30, 8194, 174, 430, 215, seed=1)
+        B = 32 if what == "step32" else (128 if what == "attnc" else 256)
+        hd, t = _mk(B, 1024, 16, 30, 8194, 174, 430, 215, seed=1, attn_compact=what == "attnc")
         for _ in range(3):
-            if what == "attn":
+            if what in ("attn", "attnc"):
                 hd.step(phase_mask=4, layer_begin=15, layer_end=16)
             else:
                 hd.step()

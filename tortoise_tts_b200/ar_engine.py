@@ -66,9 +66,11 @@ class AREngine:
     # its phases grow with the batch (2.8 / 3.7 / 4.1 ms at 64 / 128 / 256 against 2.2 / 2.4 / 3.1): one CTA per SM
     # serialises TMA wait -> MMA -> epilogue inside a phase, which several small kernels per SM overlap. "mixed" = the
     # per-op graph with its three attention kernels (prefix flash + candidate stream + merge, 65 us at 256 candidates)
-    # replaced by the persistent kernel's attention phase (one launch, 54 us). "auto" picks by batch size.
+    # replaced by the persistent kernel's attention phase (one launch, 54 us). "auto" picks by batch size. End of round 2
+    # (PDL with tail / early triggers, the tensor-core attention kernel): the mixed step also wins at 32 candidates (AR 690
+    # against 847 ms for 429 steps), so the one-kernel step is kept for small batches only (one sequence: 1.59 ms / token).
     MODE = _os.environ.get("TTB_AR_MODE", "auto")            # auto | fused | mixed | perop
-    FUSED_MAX_B = int(_os.environ.get("TTB_AR_FUSED_MAX_B", "40"))
+    FUSED_MAX_B = int(_os.environ.get("TTB_AR_FUSED_MAX_B", "16"))
     # TTB_AR_CHAINS=2: in mixed mode the candidates are decoded as TWO independent half-batches on two streams inside
     # one captured step. Every kernel of the chain LN -> c_attn -> attention -> c_proj -> LN -> c_fc -> mlp.c_proj is
     # bound by its own latency except the attention (HBM-bound), so the chain of one half fills the bubbles of the
