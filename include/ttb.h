@@ -137,7 +137,8 @@ int ttb_attention(const TtbAttnArgs* args, void* stream);
 typedef struct TtbArState {      /* device-resident, 64 ints */
   int step;                      /* number of tokens already sampled per candidate */
   int all_finished;
-  int reserved[62];
+  int reserved[62];              /* [0]: != 0 after a decode step = an internal wait of ar_step_kernel timed out;
+                                    [1]: block ticket of ttb_ar_sample (0 between launches) */
 } TtbArState;
 
 /* emb[b] = mel_embedding[tok[b]] + mel_pos_embedding[pos(step)] (autoregressive.py:145-149). pos_mode 0 =

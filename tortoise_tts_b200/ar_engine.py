@@ -80,8 +80,8 @@ class AREngine:
     WSTATIC = _os.environ.get("TTB_AR_WSTATIC", "ln")
     CHAINS = int(_os.environ.get("TTB_AR_CHAINS", "2"))     # measured: AR 1157 -> 1092 ms at 256 candidates, 860 -> 840 at 128
     CHAINS_MIN_B = int(_os.environ.get("TTB_AR_CHAINS_MIN_B", "128"))
-    SPLITK_PROJ = 2     # attn.c_proj  (K = D):   32 n-tiles x 2 m-tiles x 2 splits = 128 CTAs at D=1024, B=256
-    SPLITK_PROJ2 = 4    # mlp.c_proj   (K = 4D):  32 x 2 x 4 = 256 CTAs
+    SPLITK_PROJ = int(_os.environ.get("TTB_AR_SPLITK_PROJ", "2"))     # attn.c_proj (K = D): 32 n-tiles x 2 m-tiles x 2 splits = 128 CTAs at D=1024, B=256
+    SPLITK_PROJ2 = int(_os.environ.get("TTB_AR_SPLITK_PROJ2", "4"))   # mlp.c_proj (K = 4D): 32 x 2 x 4 = 256 CTAs
 
     @staticmethod
     def _nsplit(kb_total, splitk):

@@ -41,25 +41,26 @@ TTB_DEVINL uint32_t f2key(float f) {
 __global__ void __launch_bounds__(SAMP_THREADS)
 ar_sample_kernel(const float* __restrict__ logits, int ld_logits, int V, const float* __restrict__ uniforms, int ld_u,
                  uint32_t* __restrict__ seen, int* __restrict__ codes, int ld_codes, int* __restrict__ finished,
-                 const TtbArState* __restrict__ state, float temperature, int top_k, float top_p, float rep_penalty,
-                 int stop_token) {
+                 TtbArState* __restrict__ state, float temperature, int top_k, float top_p, float rep_penalty,
+                 int stop_token, int advance) {
   extern __shared__ float sval[];           // V floats: processed scores
   __shared__ int hist[256];
   __shared__ uint32_t s_prefix;
   __shared__ int s_remaining;
+  __shared__ int s_eq;                      // elements whose key equals the threshold key (known after the last pass)
   __shared__ float cand_v[SAMP_CAP];
   __shared__ int cand_i[SAMP_CAP];
   __shared__ int s_ncand;
   const int b = blockIdx.x;
   const int step = state->step;
   const int words = (V + 31) >> 5;
+  const int lane = threadIdx.x & 31;
   uint32_t* myseen = seen + (long long)b * words;
   const float* lrow = logits + (long long)b * ld_logits;
   if (finished[b]) {
     // HF: finished rows keep emitting pad_token_id (= stop token) (stream_generator.py:974-981)
     if (threadIdx.x == 0) codes[(long long)b * ld_codes + step] = stop_token;
-    return;
-  }
+  } else {
   for (int i = threadIdx.x; i < V; i += SAMP_THREADS) {
     float s = lrow[i];
     if ((myseen[i >> 5] >> (i & 31)) & 1u) s = (s < 0.f) ? s * rep_penalty : s / rep_penalty;
@@ -67,31 +68,71 @@ ar_sample_kernel(const float* __restrict__ logits, int ld_logits, int V, const f
   }
   if (threadIdx.x == 0) { s_prefix = 0; s_remaining = min(top_k, V); s_ncand = 0; }
   __syncthreads();
-  // radix select: find key T of the k-th largest element
+  // radix select: find key T of the k-th largest element. The histogram updates are aggregated per warp (the keys of a
+  // logit row share their exponent byte: unaggregated, pass 0 is ~8000 atomics on two or three shared-memory words), and
+  // the bin scan is done by one warp (8 bins per lane + a suffix scan) instead of a 256-step loop of one thread.
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
     hist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t prefix = s_prefix;
     const uint32_t mask = (pass == 0) ? 0u : (0xFFFFFFFFu << (shift + 8));
-    for (int i = threadIdx.x; i < V; i += SAMP_THREADS) {
-      const uint32_t k = f2key(sval[i]);
-      if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255], 1);
+    for (int base = 0; base < V; base += SAMP_THREADS) {          // uniform trip count: every lane takes part in the match
+      const int i = base + threadIdx.x;
+      int bin = 256;
+      if (i < V) {
+        const uint32_t k = f2key(sval[i]);
+        if ((k & mask) == prefix) bin = (int)((k >> shift) & 255u);
+      }
+      const unsigned peers = __match_any_sync(0xffffffffu, bin);
+      if (bin < 256 && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      int rem = s_remaining;
-      int d = 255;
-      for (; d > 0; --d) {
-        if (hist[d] >= rem) break;
-        rem -= hist[d];
+    if (threadIdx.x < 32) {
+      // bins 255 .. 0 in descending order: the bin d with  sum(hist[d+1 ..]) < remaining <= sum(hist[d ..])
+      int h[8];
+      int mine = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { h[j] = hist[lane * 8 + j]; mine += h[j]; }
+      int above = mine;                     // inclusive suffix sum over the lanes (lane 31 = the highest bins)
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_down_sync(0xffffffffu, above, o); if (lane + o < 32) above += t; }
+      above -= mine;                        // elements in bins above this lane's
+      const int rem = s_remaining;
+      const bool here = (above < rem) && (rem <= above + mine);
+      const unsigned found = __ballot_sync(0xffffffffu, here);
+      if (found) {
+        if (here) {
+          int r = rem - above, d = 7;
+          for (; d > 0; --d) {
+            if (h[d] >= r) break;
+            r -= h[d];
+          }
+          s_prefix = prefix | ((uint32_t)(lane * 8 + d) << shift);
+          s_remaining = r;
+          s_eq = h[d];
+        }
+      } else if (lane == 0) {               // fewer matching elements than requested (cannot happen for top_k <= V)
+        s_prefix = prefix;
+        s_remaining = rem - (above + mine - h[0]);
+        s_eq = h[0];
       }
-      s_prefix = prefix | ((uint32_t)d << shift);
-      s_remaining = rem;
     }
     __syncthreads();
   }
   const uint32_t thr = s_prefix;  // key of the k-th largest; HF keeps everything >= it (ties included)
+  const int n_ge = (min(top_k, V) - s_remaining) + s_eq;     // elements with key >= thr
+  if (n_ge <= SAMP_CAP) {
+    // the common case: everything that is kept fits; slot order is irrelevant (sorted below by value, then index)
+    for (int i = threadIdx.x; i < V; i += SAMP_THREADS) {
+      const float s = sval[i];
+      if (f2key(s) >= thr) {
+        const int slot = atomicAdd(&s_ncand, 1);
+        cand_v[slot] = s; cand_i[slot] = i;
+      }
+    }
+    __syncthreads();
+  } else {
   // values strictly above the threshold: at most top_k - 1 < SAMP_CAP of them, slot order is irrelevant (sorted below)
   for (int i = threadIdx.x; i < V; i += SAMP_THREADS) {
     const float s = sval[i];
@@ -118,8 +159,8 @@ ar_sample_kernel(const float* __restrict__ logits, int ld_logits, int V, const f
     if (threadIdx.x == 0) s_ncand = n;
   }
   __syncthreads();
+  }
   if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
     const int n = min(s_ncand, SAMP_CAP);
     // two elements per lane; bitonic sort of 64, descending by value then ascending by index
     float v0 = (lane < n) ? cand_v[lane] : -INFINITY, v1 = (lane + 32 < n) ? cand_v[lane + 32] : -INFINITY;
@@ -179,18 +220,28 @@ ar_sample_kernel(const float* __restrict__ logits, int ld_logits, int V, const f
       if (tok == stop_token) finished[b] = 1;
     }
   }
-}
-
-__global__ void ar_sample_advance_kernel(TtbArState* state, const int* __restrict__ finished, int B) {
-  __shared__ int any_unfinished;
-  if (threadIdx.x == 0) any_unfinished = 0;
-  __syncthreads();
-  for (int i = threadIdx.x; i < B; i += blockDim.x)
-    if (!finished[i]) any_unfinished = 1;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    state->step += 1;
-    state->all_finished = any_unfinished ? 0 : 1;
+  }   // !finished[b]
+  if (advance) {
+    // the last block to get here advances the step counter (every block read it at its start) and refreshes the
+    // all-finished flag: what the separate ar_sample_advance_kernel launch did, without the launch
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = (atomicAdd(&state->reserved[1], 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      int unf = 0;
+      for (int i = threadIdx.x; i < (int)gridDim.x; i += SAMP_THREADS) unf |= (__ldcg(finished + i) == 0);
+      unf = __syncthreads_or(unf);
+      if (threadIdx.x == 0) {
+        state->reserved[1] = 0;
+        state->all_finished = unf ? 0 : 1;
+        state->step = step + 1;
+      }
+    }
   }
 }
 
@@ -241,12 +292,8 @@ extern "C" int ttb_ar_sample(const float* logits, int ld_logits, int V, int B, c
   const size_t smem = (size_t)V * sizeof(float);
   if (smem > 40 * 1024) { set_error("ttb_ar_sample: vocabulary %d too large", V); return -1; }
   ar_sample_kernel<<<B, SAMP_THREADS, smem, st>>>(logits, ld_logits, V, uniforms, ld_u, seen, codes, ld_codes, finished,
-                                                  state, temperature, top_k, top_p, rep_penalty, stop_token);
+                                                  state, temperature, top_k, top_p, rep_penalty, stop_token, advance ? 1 : 0);
   TTB_CHECK_LAUNCH("ar_sample_kernel");
-  if (advance) {
-    ar_sample_advance_kernel<<<1, 256, 0, st>>>(state, finished, B);
-    TTB_CHECK_LAUNCH("ar_sample_advance_kernel");
-  }
   return 0;
 }
 

@@ -45,7 +45,6 @@ template <int MINB, bool DBUF = false>
 __global__ void __launch_bounds__(FA_THREADS, MINB)
 flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                      const __grid_constant__ CUtensorMap map_v, TtbAttnArgs a) {
-  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FaSmem::BAR_OFF);
@@ -87,6 +86,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();        // barrier init, TMEM allocation and descriptor prefetch above overlap the tail of the qkv GEMM
   const uint32_t tmem_s = tmem_base;                        // columns [0, 64) (+ [64, 128) with DBUF)
   const uint32_t tmem_o = tmem_base + (DBUF ? 128 : 64);    // 64 columns
 

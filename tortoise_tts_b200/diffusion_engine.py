@@ -166,6 +166,9 @@ class DiffusionEngine:
         self.GN_FUSED = int(os.environ.get("TTB_GN_FUSED", "1"))
         # the two CFG branches as two kernel chains on two streams instead of one batched pass (see _forward)
         self.CHAINS = int(os.environ.get("TTB_DIFF_CHAINS", "0"))
+        # the C x C GEMMs of a step put their first weight tiles into the pipeline ahead of griddepcontrol.wait
+        # (TtbGemmArgs.w_static; the GroupNorm in front of them releases its dependents early): 618 -> 616 ms, TTB_DIFF_WSTATIC=0 = off
+        self.WS = bool(int(os.environ.get("TTB_DIFF_WSTATIC", "1")))
 
     # ------------------------------------------------------------------ building blocks on [B, S, C] fp32 (in place)
     def _gn(self, x, B, S, g, b, ws, silu=False, ss=None, ss_row=None, out=None, ready=False):
@@ -188,12 +191,12 @@ class DiffusionEngine:
         gp = self._gnp(S, ws)
         self._gn(x, B, S, aw.gn_g, aw.gn_b, ws, ready=ready)
         lib.gemm(ws["a"], aw.wqkv, M=S, N=3 * C, K=C, bias=aw.bqkv, out_bf16=ws["qkv"], batch=B, a_bstride=S * C,
-                 outb_bstride=S * 3 * C, cluster=self.CL)
+                 outb_bstride=S * 3 * C, cluster=self.CL, w_static=self.WS)
         # T5 buckets saturate at max_distance = 64 (xtransformers.py:166-174): |j - i| >= 64 -> constant bias per side
         lib.attention(ws["qkv"], ws["o"], nseq=B, T=S, H=H, ld=3 * C, ldo=C, k_off=C, v_off=2 * C, scale=0.125,
                       bias=aw.table(S), bias_sat=64)
         lib.gemm(ws["o"], aw.wproj, M=S, N=C, K=C, bias=aw.bproj, residual=x, out_f32=x, batch=B, a_bstride=S * C,
-                 res_bstride=S * C, outf_bstride=S * C, cluster=self.CL, **gp)
+                 res_bstride=S * C, outf_bstride=S * C, cluster=self.CL, w_static=self.WS, **gp)
         return bool(gp)
 
     def _res_block(self, rw, ss, x, B, S, ws, ss_row=None, ready=False):
@@ -202,10 +205,10 @@ class DiffusionEngine:
         gp = self._gnp(S, ws)
         self._gn(x, B, S, rw.in_g, rw.in_b, ws, silu=True, ready=ready)
         lib.gemm(ws["a"], rw.w_in, M=S, N=C, K=C, bias=rw.b_in, out_f32=ws["h"], batch=B, a_bstride=S * C,
-                 outf_bstride=S * C, cluster=self.CL, **gp)
+                 outf_bstride=S * C, cluster=self.CL, w_static=self.WS, **gp)
         self._gn(ws["h"], B, S, rw.out_g, rw.out_b, ws, silu=True, ss=ss, ss_row=ss_row, ready=bool(gp))
         lib.gemm(ws["a"], rw.w_out, M=S, N=C, K=C, taps=3, pad=1, bias=rw.b_out, residual=x, out_f32=x, batch=B,
-                 a_bstride=S * C, res_bstride=S * C, outf_bstride=S * C, cluster=self.CL, **gp)
+                 a_bstride=S * C, res_bstride=S * C, outf_bstride=S * C, cluster=self.CL, w_static=self.WS, **gp)
         return bool(gp)
 
     def _alloc(self, B, S):

@@ -3,8 +3,9 @@
 No trained weights are reachable offline, so benchmarks and parity tests run on seeded
 random weights with exactly the tensor names/shapes the reference modules produce
 (`tortoise/api.py:217-238`).  Nothing here instantiates a reference module: the names are
-generated from the layout, and `tests/test_synth_layout.py` checks (in the build container,
-where the reference is importable) that they load into the reference modules strictly.
+generated from the layout; `oracle/ref_build.py` (used by `tests/test_oracle_vs_reference.py` in the build container,
+where the reference is importable) loads them into the reference modules with `strict=True`, and
+`tests/test_host_logic.py::test_synth_layout_param_counts` checks the parameter counts of SURVEY App. B anywhere.
 
 Conventions: zero-initialised tensors of the reference (AttentionBlock.proj_out,
 arch_util.py:111) are drawn N(0, .02) so attention is exercised; norm affines are jittered;
