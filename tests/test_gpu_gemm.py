@@ -178,8 +178,9 @@ EXPERIMENTAL = [
 
 
 @pytest.mark.skipif(__import__("os").environ.get("TTB_TEST_EXPERIMENTAL") != "1",
-                    reason="round-2 kernels (variants 5, 6) have not run on hardware yet: opt in with TTB_TEST_EXPERIMENTAL=1 "
-                           "and run under `timeout` (a protocol bug in the CTA-pair kernel would hang)")
+                    reason="GEMM variants 5 / 6 (two TMA issuers, CTA pair) are not on the product path (they ran correctly on "
+                           "B200 in round 2 and lost to the default kernel, profiles/gemm_sweep_r02_with_2cta.txt): opt in with "
+                           "TTB_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("case", EXPERIMENTAL, ids=[str(i) for i in range(len(EXPERIMENTAL))])
 def test_gemm_experimental_variants(case):
     y, of, ob = _run(**case)
