@@ -12,6 +12,7 @@ Deliberate differences: sampling randomness comes from a device 
 `use_deterministic_seed`; `tts_with_preset` drops the diffusion-only preset keys instead of forwarding them to HF
 `generate` (which rejects them in the reference); the wav2vec redaction model is not loaded.
 """
+import os
 import random
 from time import time
 
@@ -23,9 +24,9 @@ from .conditioning_engine import ConditioningEngine, RandomLatentEngine
 from .hifigan_engine import HifiganEngine
 from . import lib
 from . import parallel
-from .api import MODELS_DIR, _Tokenizer, _default_mel_norms, get_model_path as _api_model_path, pad_or_truncate  # noqa: F401
-from .api import format_conditioning, pick_best_batch_size_for_gpu  # noqa: F401  (module-level names of api_fast.py)
-import os
+from .api import MODELS_DIR, _Tokenizer, _default_mel_norms
+# module-level names callers of tortoise/api_fast.py import from it (api_fast.py:52-171)
+from .api import pad_or_truncate, format_conditioning, pick_best_batch_size_for_gpu, classify_audio_clip  # noqa: F401
 
 MODELS = ("autoregressive.pth", "classifier.pth", "clvp2.pth", "cvvp.pth", "diffusion_decoder.pth", "vocoder.pth",
           "rlg_auto.pth", "rlg_diffuser.pth", "hifidecoder.pth")       # api_fast.py:31-43
