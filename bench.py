@@ -298,6 +298,9 @@ def run_engine(args):
         workload = ("configs[2]: preset='%s' (%d AR samples, %d diffusion iters), %d-token paragraph, N=%d mel tokens -> "
                     "%.2f s audio, k=1" % (preset, B, iters, len(tokens), n_mel, audio_s))
         par = "candidates sharded %d/GPU; CFG branch pair on 2 GPUs for the k=1 diffusion tail" % ((B + world - 1) // world)
+        dec = getattr(tts.autoregressive, "_dec", None)       # how the decode step of this run was organised
+        if dec is not None:
+            par += "; decode step: %s, %d chain(s) per GPU" % (dec["mode"], len(dec["chains"]))
     line = {
         "metric": METRIC if not config5 else "audio-seconds/sec at preset='high_quality' (8 utterances)",
         "value": audio_s / (dev_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
