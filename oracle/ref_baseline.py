@@ -36,9 +36,23 @@ def _t(fn, dev, reps=1):
     return best
 
 
+_MODELS = {}
+
+
+def _models(cfg, sds, dev):
+    """The reference modules, built ONCE per process and device: a run of `--repeat n` samples re-times the unit costs n
+    times on the same modules instead of constructing 1.2 G parameters per sample (the reference arm of bench.py has to
+    fit n = warmup + steps samples into a few minutes)."""
+    key = dev.type
+    if key not in _MODELS:
+        from .ref_build import build_reference_models
+        mods = build_reference_models(cfg, sds, kv_cache=True)
+        _MODELS[key] = tuple(mods[k].to(dev) for k in ("autoregressive", "clvp", "diffusion", "vocoder"))
+    return _MODELS[key]
+
+
 def measure(cfg, sds, text_tokens, num_candidates=256, n_mel=430, iters=200, cond_free=True, device="cpu", threads=None,
             gen_points=None, clvp_rows=None):
-    from .ref_build import build_reference_models
     dev = torch.device(device)
     if threads and dev.type == "cpu":
         torch.set_num_threads(threads)
@@ -46,8 +60,7 @@ def measure(cfg, sds, text_tokens, num_candidates=256, n_mel=430, iters=200, con
         gen_points = (8, 40) if dev.type == "cuda" else (2, 5)
     if clvp_rows is None:
         clvp_rows = 16 if dev.type == "cuda" else 2
-    mods = build_reference_models(cfg, sds, kv_cache=True)
-    ar, clvp, diff, voc = (mods[k].to(dev) for k in ("autoregressive", "clvp", "diffusion", "vocoder"))
+    ar, clvp, diff, voc = _models(cfg, sds, dev)
     torch.manual_seed(0)
     bs = 16
     cond = (torch.randn(1, cfg.ar_dim) * 0.5).to(dev)
